@@ -1,0 +1,69 @@
+// Shared host/device helpers for libdmhomo (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/dmhomo.h"
+
+namespace dmh {
+
+// ---- host side -----------------------------------------------------------------------
+extern thread_local char g_last_error[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// Call right after a <<<>>> launch: counts it and turns launch errors into DMH_ECUDA.
+inline int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DMH_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return DMH_OK;
+}
+
+#define DMH_REQUIRE(cond, ...) \
+  do {                         \
+    if (!(cond)) return ::dmh::fail(DMH_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- device side ----------------------------------------------------------------------
+// Separately rounded fp32 arithmetic: the reference is a chain of individually rounded
+// ATen elementwise ops, so bit-exact coordinates / indices / masks need "no FMA
+// contraction" spelled out.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sign_of(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+// fire-and-forget fp32 add (SASS: REDG.E.ADD.F32)
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+
+}  // namespace dmh

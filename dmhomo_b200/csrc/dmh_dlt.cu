@@ -1,0 +1,196 @@
+// 4-point DLT: one warp per 8x8 system, the augmented matrix lives in registers
+// (lane r < 8 owns row r), partial pivoting and back-substitution through warp shuffles.
+//
+// Replaces DLT.forward(method='Axb') / WarpMat / DLT_solve:
+//   HEM/model/utils.py:55-101, 19-43, 360-397; HEM/model/net.py:24-92.
+// The reference forms inverse(A) @ b in fp32 (LU); its own error against the exact solution
+// of its fp32 system is ~1e-7 (Frobenius-relative).  We build A with the reference's fp32
+// roundings (entries -(u*x) rounded once), then eliminate in fp64 so that the only
+// difference to the reference is the reference's own rounding noise.
+#include "dmh_common.cuh"
+
+namespace dmh {
+
+// Solves M z = rhs for the 8x8 system whose row `lane` (lane < 8) is m[0..7] | m[8].
+// Returns z_k broadcast in sol[k] on every lane.
+__device__ __forceinline__ void solve8_warp(double (&m)[9], int lane, double (&sol)[8]) {
+  bool used = false;
+  int piv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // pivot search: largest |m[k]| among unused rows, lowest lane wins ties
+    double best = (lane < 8 && !used) ? fabs(m[k]) : -1.0;
+    int who = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+      if (ob > best || (ob == best && ow < who)) {
+        best = ob;
+        who = ow;
+      }
+    }
+    piv[k] = who;
+    const double pk = __shfl_sync(0xffffffffu, m[k], who);
+    const bool elim = (lane < 8) && !used && (lane != who);
+    const double f = elim ? m[k] / pk : 0.0;
+#pragma unroll
+    for (int j = k + 1; j < 9; ++j) {
+      const double pj = __shfl_sync(0xffffffffu, m[j], who);
+      if (elim) m[j] = fma(-f, pj, m[j]);
+    }
+    if (lane == who) used = true;
+  }
+#pragma unroll
+  for (int k = 7; k >= 0; --k) {
+    double acc = m[8];
+#pragma unroll
+    for (int j = k + 1; j < 8; ++j) acc = fma(-m[j], sol[j], acc);
+    const double xk = acc / m[k];
+    sol[k] = __shfl_sync(0xffffffffu, xk, piv[k]);
+  }
+}
+
+// Row `r` (0..7) of the DLT system for point i = r/2 (App. A.1).
+__device__ __forceinline__ void dlt_row(int r, float x, float y, float u, float v, double (&m)[9]) {
+  const bool top = (r & 1) == 0;
+  const float t = top ? u : v;
+  m[0] = top ? x : 0.f;
+  m[1] = top ? y : 0.f;
+  m[2] = top ? 1.f : 0.f;
+  m[3] = top ? 0.f : x;
+  m[4] = top ? 0.f : y;
+  m[5] = top ? 0.f : 1.f;
+  m[6] = (double)(-mul_rn(t, x));
+  m[7] = (double)(-mul_rn(t, y));
+  m[8] = t;
+}
+
+__global__ void __launch_bounds__(128) dlt4_fwd_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                                                       float* __restrict__ H, int N) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int r = lane & 7, i = r >> 1;
+  const float x = __ldg(src + (size_t)n * 8 + 2 * i), y = __ldg(src + (size_t)n * 8 + 2 * i + 1);
+  const float u = __ldg(dst + (size_t)n * 8 + 2 * i), v = __ldg(dst + (size_t)n * 8 + 2 * i + 1);
+  double m[9], sol[8];
+  dlt_row(r, x, y, u, v, m);
+  solve8_warp(m, lane, sol);
+  if (lane < 8) H[(size_t)n * 9 + lane] = (float)sol[lane];
+  if (lane == 8) H[(size_t)n * 9 + 8] = 1.0f;
+}
+
+// h = A^-1 b.  With z = A^-T g_h:
+//   g_u_i = z[2i] (1 + x_i h6 + y_i h7),  g_v_i = z[2i+1] (1 + x_i h6 + y_i h7)
+//   g_x_i = -z[2i] (h0 - u_i h6) - z[2i+1] (h3 - v_i h6),  g_y_i = -z[2i] (h1 - u_i h7) - z[2i+1] (h4 - v_i h7)
+__global__ void __launch_bounds__(128) dlt4_bwd_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                                                       const float* __restrict__ H, const float* __restrict__ gH,
+                                                       float* __restrict__ g_dst, float* __restrict__ g_src, int N) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int r = lane & 7;
+  // row r of A^T = column r of A
+  double m[9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = j >> 1;
+    const float x = __ldg(src + (size_t)n * 8 + 2 * i), y = __ldg(src + (size_t)n * 8 + 2 * i + 1);
+    const float u = __ldg(dst + (size_t)n * 8 + 2 * i), v = __ldg(dst + (size_t)n * 8 + 2 * i + 1);
+    double row[9];
+    dlt_row(j, x, y, u, v, row);
+    m[j] = row[r];
+  }
+  m[8] = (double)__ldg(gH + (size_t)n * 9 + r);
+  double z[8];
+  solve8_warp(m, lane, z);
+  if (lane < 4) {
+    const int i = lane;
+    const double x = __ldg(src + (size_t)n * 8 + 2 * i), y = __ldg(src + (size_t)n * 8 + 2 * i + 1);
+    const double u = __ldg(dst + (size_t)n * 8 + 2 * i), v = __ldg(dst + (size_t)n * 8 + 2 * i + 1);
+    const double h0 = __ldg(H + (size_t)n * 9 + 0), h1 = __ldg(H + (size_t)n * 9 + 1);
+    const double h3 = __ldg(H + (size_t)n * 9 + 3), h4 = __ldg(H + (size_t)n * 9 + 4);
+    const double h6 = __ldg(H + (size_t)n * 9 + 6), h7 = __ldg(H + (size_t)n * 9 + 7);
+    double zt = 0.0, zb = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // static register indexing
+      if (q == i) {
+        zt = z[2 * q];
+        zb = z[2 * q + 1];
+      }
+    }
+    const double s = 1.0 + x * h6 + y * h7;
+    g_dst[(size_t)n * 8 + 2 * i] = (float)(zt * s);
+    g_dst[(size_t)n * 8 + 2 * i + 1] = (float)(zb * s);
+    if (g_src) {
+      g_src[(size_t)n * 8 + 2 * i] = (float)(-zt * (h0 - u * h6) - zb * (h3 - v * h6));
+      g_src[(size_t)n * 8 + 2 * i + 1] = (float)(-zt * (h1 - u * h7) - zb * (h4 - v * h7));
+    }
+  }
+}
+
+// ---- basis flow at the four image corners (cfg 2 "DLT step") ---------------------------------
+// offsets[b, corner, xy] = sum_k basis[k, xy, corner] * w[b,k], sequential, separately rounded.
+__global__ void basis_corner_fwd_kernel(const float* __restrict__ basis, const float* __restrict__ weight,
+                                        float* __restrict__ off, int B, int h, int w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * 8) return;
+  const int b = t >> 3, c = (t >> 1) & 3, xy = t & 1;
+  const int py = (c >> 1) ? h - 1 : 0, px = (c & 1) ? w - 1 : 0;
+  const size_t plane = (size_t)h * w, po = (size_t)py * w + px;
+  float acc = mul_rn(__ldg(basis + (size_t)xy * plane + po), __ldg(weight + b * 8));
+  for (int k = 1; k < 8; ++k)
+    acc = add_rn(acc, mul_rn(__ldg(basis + (size_t)(2 * k + xy) * plane + po), __ldg(weight + b * 8 + k)));
+  off[t] = acc;
+}
+
+__global__ void basis_corner_bwd_kernel(const float* __restrict__ basis, const float* __restrict__ g_off,
+                                        float* __restrict__ g_w, int B, int h, int w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * 8) return;
+  const int b = t >> 3, k = t & 7;
+  const size_t plane = (size_t)h * w;
+  float acc = 0.f;
+  for (int c = 0; c < 4; ++c) {
+    const int py = (c >> 1) ? h - 1 : 0, px = (c & 1) ? w - 1 : 0;
+    const size_t po = (size_t)py * w + px;
+    acc += __ldg(g_off + b * 8 + c * 2) * __ldg(basis + (size_t)(2 * k) * plane + po);
+    acc += __ldg(g_off + b * 8 + c * 2 + 1) * __ldg(basis + (size_t)(2 * k + 1) * plane + po);
+  }
+  red_add(g_w + t, acc);
+}
+
+}  // namespace dmh
+
+extern "C" int dmh_dlt4_forward(const float* src, const float* dst, float* H, int N, void* stream) {
+  DMH_REQUIRE(src && dst && H, "dlt4_forward: null pointer");
+  DMH_REQUIRE(N > 0, "dlt4_forward: N must be positive");
+  dmh::dlt4_fwd_kernel<<<(N + 3) / 4, 128, 0, dmh::as_stream(stream)>>>(src, dst, H, N);
+  return dmh::launched("dlt4_fwd_kernel");
+}
+
+extern "C" int dmh_dlt4_backward(const float* src, const float* dst, const float* H, const float* grad_H,
+                                 float* grad_dst, float* grad_src, int N, void* stream) {
+  DMH_REQUIRE(src && dst && H && grad_H && grad_dst, "dlt4_backward: null pointer");
+  DMH_REQUIRE(N > 0, "dlt4_backward: N must be positive");
+  dmh::dlt4_bwd_kernel<<<(N + 3) / 4, 128, 0, dmh::as_stream(stream)>>>(src, dst, H, grad_H, grad_dst, grad_src, N);
+  return dmh::launched("dlt4_bwd_kernel");
+}
+
+extern "C" int dmh_basis_corner_offsets(const float* basis, const float* weight, float* offsets, int B, int h, int w,
+                                        void* stream) {
+  DMH_REQUIRE(basis && weight && offsets, "basis_corner_offsets: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "basis_corner_offsets: non-positive size");
+  dmh::basis_corner_fwd_kernel<<<(B * 8 + 127) / 128, 128, 0, dmh::as_stream(stream)>>>(basis, weight, offsets, B, h, w);
+  return dmh::launched("basis_corner_fwd_kernel");
+}
+
+extern "C" int dmh_basis_corner_offsets_backward(const float* basis, const float* grad_offsets, float* grad_weight,
+                                                 int B, int h, int w, void* stream) {
+  DMH_REQUIRE(basis && grad_offsets && grad_weight, "basis_corner_offsets_backward: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "basis_corner_offsets_backward: non-positive size");
+  dmh::basis_corner_bwd_kernel<<<(B * 8 + 127) / 128, 128, 0, dmh::as_stream(stream)>>>(basis, grad_offsets,
+                                                                                      grad_weight, B, h, w);
+  return dmh::launched("basis_corner_bwd_kernel");
+}

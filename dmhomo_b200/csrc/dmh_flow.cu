@@ -1,0 +1,501 @@
+// Elementwise / reduction kernels around the warp: homography -> flow (fp32 and fp64 variants),
+// basis-flow combine, validity masks, plain L1, loss finish, flow -> RGB, evaluation point error.
+#include "dmh_common.cuh"
+
+namespace dmh {
+
+constexpr int kThreads = 256;
+
+static inline unsigned blocks_for(long long n, int per_block = kThreads) {
+  long long b = (n + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * 32;  // grid-stride beyond a few waves
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ---- A5: get_flow (HEM/model/utils.py:400-440) -------------------------------------------------
+__device__ __forceinline__ void h2flow(const float* hm, float gx, float gy, float& fx, float& fy, float& qX,
+                                       float& qY, float& qT) {
+  qX = add_rn(add_rn(mul_rn(hm[0], gx), mul_rn(hm[1], gy)), hm[2]);
+  qY = add_rn(add_rn(mul_rn(hm[3], gx), mul_rn(hm[4], gy)), hm[5]);
+  qT = add_rn(add_rn(mul_rn(hm[6], gx), mul_rn(hm[7], gy)), hm[8]);
+  if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
+  fx = sub_rn(div_rn(qX, qT), gx);
+  fy = sub_rn(div_rn(qY, qT), gy);
+}
+
+__global__ void __launch_bounds__(kThreads) h2flow_fwd_kernel(const float* __restrict__ H, float* __restrict__ flow,
+                                                              int B, int h, int w, int dv, float sx, float sy,
+                                                              const float* __restrict__ start) {
+  const long long plane = (long long)h * w, total = plane * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+    const int cell = (dv == 1) ? 0 : (min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1));
+    const float* hp = H + ((size_t)b * dv * dv + cell) * 9;
+    float hm[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
+    float fx, fy, qX, qY, qT;
+    const float ox = start ? __ldg(start + 2 * b) : sx, oy = start ? __ldg(start + 2 * b + 1) : sy;
+    h2flow(hm, add_rn((float)x, ox), add_rn((float)y, oy), fx, fy, qX, qY, qT);
+    flow[((size_t)b * 2) * plane + p] = fx;
+    flow[((size_t)b * 2 + 1) * plane + p] = fy;
+  }
+}
+
+// grad_H[b,cell] += sum_px (gX*(gx,gy,1), gY*(gx,gy,1), gT*(gx,gy,1)); one CTA = 8 rows x 256 px of a cell row
+__global__ void __launch_bounds__(kThreads) h2flow_bwd_kernel(const float* __restrict__ H,
+                                                              const float* __restrict__ gflow, float* __restrict__ gH,
+                                                              int B, int h, int w, int dv, float sx, float sy,
+                                                              const float* __restrict__ start) {
+  // grid: (chunks of a cell's pixels, cell, b)
+  const int b = blockIdx.z, cell = blockIdx.y;
+  if (start) {
+    sx = __ldg(start + 2 * b);
+    sy = __ldg(start + 2 * b + 1);
+  }
+  const int ch = h / dv, cw = w / dv;
+  const int cy0 = (cell / dv) * ch, cx0 = (cell % dv) * cw;
+  const int cell_h = (cell / dv == dv - 1) ? h - cy0 : ch, cell_w = (cell % dv == dv - 1) ? w - cx0 : cw;
+  const long long npx = (long long)cell_h * cell_w, plane = (long long)h * w;
+  const float* hp = H + ((size_t)b * dv * dv + cell) * 9;
+  float hm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    const int yy = (int)(i / cell_w), xx = (int)(i - (long long)yy * cell_w);
+    const int y = cy0 + yy, x = cx0 + xx;
+    const float gx = add_rn((float)x, sx), gy = add_rn((float)y, sy);
+    float fx, fy, qX, qY, qT;
+    h2flow(hm, gx, gy, fx, fy, qX, qY, qT);
+    const long long p = (long long)y * w + x;
+    const float gfx = __ldg(gflow + ((size_t)b * 2) * plane + p), gfy = __ldg(gflow + ((size_t)b * 2 + 1) * plane + p);
+    const float rT = 1.f / qT;
+    const float gX = gfx * rT, gY = gfy * rT, gT = -(gfx * qX + gfy * qY) * rT * rT;
+    acc[0] += gX * gx; acc[1] += gX * gy; acc[2] += gX;
+    acc[3] += gY * gx; acc[4] += gY * gy; acc[5] += gY;
+    acc[6] += gT * gx; acc[7] += gT * gy; acc[8] += gT;
+  }
+  __shared__ float red[kThreads / 32][9];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[wrp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) v += red[q][threadIdx.x];
+    red_add(gH + ((size_t)b * dv * dv + cell) * 9 + threadIdx.x, v);
+  }
+}
+
+// ---- A15: numpy fp64 homography -> flow / mapping (ddpm.py:913-975; ...operations.py:454-484) ----
+__global__ void __launch_bounds__(kThreads) h2flow_f64_kernel(const double* __restrict__ H, float* __restrict__ out,
+                                                              int B, int h, int w, double eps, int channels_last,
+                                                              int as_mapping) {
+  const long long plane = (long long)h * w, total = plane * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+    const double* hm = H + (size_t)b * 9;
+    const double dx = (double)x, dy = (double)y;
+    const double X = __dadd_rn(__dadd_rn(__dmul_rn(hm[0], dx), __dmul_rn(hm[1], dy)), hm[2]);
+    const double Y = __dadd_rn(__dadd_rn(__dmul_rn(hm[3], dx), __dmul_rn(hm[4], dy)), hm[5]);
+    const double T = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(hm[6], dx), __dmul_rn(hm[7], dy)), hm[8]), eps);
+    double ox = __ddiv_rn(X, T), oy = __ddiv_rn(Y, T);
+    if (!as_mapping) {
+      ox = __dsub_rn(ox, dx);
+      oy = __dsub_rn(oy, dy);
+    }
+    if (channels_last) {
+      reinterpret_cast<float2*>(out)[i] = make_float2((float)ox, (float)oy);
+    } else {
+      out[((size_t)b * 2) * plane + p] = (float)ox;
+      out[((size_t)b * 2 + 1) * plane + p] = (float)oy;
+    }
+  }
+}
+
+// ---- A12: basis combine (HEM/model/net.py:808-815) ------------------------------------------------
+// One thread = one pixel; the 16 basis values stay in registers while the thread loops over the
+// batch, so the shared basis tensor is read once per launch instead of once per sample.
+__global__ void __launch_bounds__(kThreads) basis_combine_kernel(const float* __restrict__ basis,
+                                                                 const float* __restrict__ weight,
+                                                                 float* __restrict__ flow, int B, int h, int w,
+                                                                 int b_per_block) {
+  const long long plane = (long long)h * w;
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= plane) return;
+  float bx[8], by[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    bx[k] = __ldg(basis + (size_t)(2 * k) * plane + p);
+    by[k] = __ldg(basis + (size_t)(2 * k + 1) * plane + p);
+  }
+  const int b0 = blockIdx.y * b_per_block, b1 = min(B, b0 + b_per_block);
+  for (int b = b0; b < b1; ++b) {
+    const float* wp = weight + (size_t)b * 8;
+    float fx = mul_rn(bx[0], __ldg(wp)), fy = mul_rn(by[0], __ldg(wp));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float wk = __ldg(wp + k);
+      fx = add_rn(fx, mul_rn(bx[k], wk));
+      fy = add_rn(fy, mul_rn(by[k], wk));
+    }
+    flow[((size_t)b * 2) * plane + p] = fx;
+    flow[((size_t)b * 2 + 1) * plane + p] = fy;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) basis_combine_bwd_kernel(const float* __restrict__ basis,
+                                                                     const float* __restrict__ gflow,
+                                                                     float* __restrict__ gw, int B, int h, int w) {
+  const int b = blockIdx.y;
+  const long long plane = (long long)h * w;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < plane; p += (long long)gridDim.x * blockDim.x) {
+    const float gx = __ldg(gflow + ((size_t)b * 2) * plane + p), gy = __ldg(gflow + ((size_t)b * 2 + 1) * plane + p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      acc[k] += gx * __ldg(basis + (size_t)(2 * k) * plane + p) + gy * __ldg(basis + (size_t)(2 * k + 1) * plane + p);
+  }
+  __shared__ float red[kThreads / 32][8];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[wrp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) v += red[q][threadIdx.x];
+    red_add(gw + (size_t)b * 8 + threadIdx.x, v);
+  }
+}
+
+// ---- A10/A11: masks (HEM/utils_operations/flow_and_mapping_operations.py:6-71) -----------------------
+__global__ void __launch_bounds__(kThreads) border_mask_kernel(const float* __restrict__ flow, uint8_t* __restrict__ m8,
+                                                               float* __restrict__ mf, int B, int h, int w) {
+  const long long plane = (long long)h * w, total = plane * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+    const float mx = add_rn(__ldg(flow + ((size_t)b * 2) * plane + p), (float)x);
+    const float my = add_rn(__ldg(flow + ((size_t)b * 2 + 1) * plane + p), (float)y);
+    const bool ok = (mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h);
+    if (m8) m8[i] = ok ? 1 : 0;
+    if (mf) mf[i] = ok ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) zero_border_mask_kernel(const float* __restrict__ img,
+                                                                    uint8_t* __restrict__ mask, int B, int h, int w,
+                                                                    float eps) {
+  const long long plane = (long long)h * w, total = plane * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    const float* ip = img + (size_t)b * 3 * plane + p;
+    const bool occ = (__ldg(ip) <= eps) && (__ldg(ip + plane) <= eps) && (__ldg(ip + 2 * plane) <= eps);
+    mask[i] = occ ? 0 : 1;
+  }
+}
+
+// ---- A13: LossL1 (HEM/loss/losses.py:10-17) ---------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) l1_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          long long n, double* __restrict__ acc) {
+  float s = 0.f;
+  double sd = 0.0;
+  int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    s += fabsf(__ldg(a + i) - __ldg(b + i));
+    if (++cnt == 64) {  // bound the fp32 partial
+      sd += (double)s;
+      s = 0.f;
+      cnt = 0;
+    }
+  }
+  sd += (double)s;
+  sd = warp_sum(sd);
+  __shared__ double red[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) v += red[q];
+    atomicAdd(acc, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          long long n, const float* __restrict__ g, float scale,
+                                                          float* __restrict__ ga, float* __restrict__ gb) {
+  const float gs = (g ? __ldg(g) : 1.f) * scale;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = gs * sign_of(__ldg(a + i) - __ldg(b + i));
+    if (ga) ga[i] = v;
+    if (gb) gb[i] = -v;
+  }
+}
+
+struct FinishArgs {
+  const double* acc[8];
+  const float* sw[8];
+};
+
+__global__ void loss_finish_kernel(FinishArgs args, int n_acc, int B, float scale, float* __restrict__ loss) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_acc * B; i += blockDim.x) {
+    const int a = i / B, b = i - a * B;
+    const double wgt = args.sw[a] ? (double)__ldg(args.sw[a] + b) : 1.0;
+    s += wgt * args.acc[a][b];
+  }
+  s = warp_sum(s);
+  __shared__ double red[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) v += red[q];
+    loss[0] = (float)(v * (double)scale);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) scale_inplace_kernel(float* __restrict__ x, long long n,
+                                                                 const float* __restrict__ g) {
+  const float gs = __ldg(g);
+  if (gs == 1.0f) return;  // unit upstream gradient: the forward-computed gradient is already final
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= gs;
+}
+
+// ---- A16: flow_to_image (ddpm.py:1471-1486) + hsv_to_rgb (App. A.6) ---------------------------------
+__global__ void __launch_bounds__(kThreads) flow_to_rgb_kernel(const float* __restrict__ flow, float* __restrict__ rgb,
+                                                               int B, int h, int w, float max_flow, int in_cl,
+                                                               int out_cl) {
+  const long long plane = (long long)h * w, total = plane * B;
+  const float two_pi = 6.2831855f;  // float32(2*np.pi)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    float u, v;
+    if (in_cl) {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
+      u = f.x;
+      v = f.y;
+    } else {
+      u = __ldg(flow + ((size_t)b * 2) * plane + p);
+      v = __ldg(flow + ((size_t)b * 2 + 1) * plane + p);
+    }
+    const float mag = __fsqrt_rn(add_rn(mul_rn(u, u), mul_rn(v, v)));
+    const float ang = atan2f(v, u);
+    float hh = add_rn(div_rn(ang, two_pi), 1.0f);
+    hh = hh - floorf(hh);                        // np.mod(., 1) for a value in [0.5, 1.5]
+    const float s = fminf(fmaxf(div_rn(mul_rn(mag, 8.0f), max_flow), 0.f), 1.f);
+    const float val = fminf(fmaxf(sub_rn(8.0f, s), 0.f), 1.f);
+    // hsv_to_rgb
+    const float h6 = mul_rn(hh, 6.0f);
+    const int sec = (int)h6;
+    const float f = sub_rn(h6, (float)sec);
+    const float pp = mul_rn(val, sub_rn(1.f, s));
+    const float qq = mul_rn(val, sub_rn(1.f, mul_rn(s, f)));
+    const float tt = mul_rn(val, sub_rn(1.f, mul_rn(s, sub_rn(1.f, f))));
+    float r, g, bl;
+    switch (sec % 6) {
+      case 0: r = val; g = tt; bl = pp; break;
+      case 1: r = qq; g = val; bl = pp; break;
+      case 2: r = pp; g = val; bl = tt; break;
+      case 3: r = pp; g = qq; bl = val; break;
+      case 4: r = tt; g = pp; bl = val; break;
+      default: r = val; g = pp; bl = qq; break;
+    }
+    if (s == 0.f) r = g = bl = val;
+    if (out_cl) {
+      float* o = rgb + (size_t)i * 3;
+      o[0] = r; o[1] = g; o[2] = bl;
+    } else {
+      float* o = rgb + (size_t)b * 3 * plane + p;
+      o[0] = r; o[plane] = g; o[2 * plane] = bl;
+    }
+  }
+}
+
+// ---- A18: ComputeErrFlow / compute_eval_results (HEM/loss/losses.py:208-211, 263-296) ------------------
+__global__ void eval_point_error_kernel(const float* __restrict__ pts, const float* __restrict__ ff,
+                                        const float* __restrict__ fb, float* __restrict__ err, int B, int P, int h,
+                                        int w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float tot = 0.f;
+  for (int j = 0; j < P; ++j) {
+    const float* q = pts + ((size_t)b * P + j) * 4;
+    const float p1x = q[0], p1y = q[1], p2x = q[2], p2y = q[3];
+    float e[2];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const float sx_ = dir ? p2x : p1x, sy_ = dir ? p2y : p1y, dx_ = dir ? p1x : p2x, dy_ = dir ? p1y : p2y;
+      const float* fl = dir ? fb : ff;
+      int iy = (int)sy_, ix = (int)sx_;          // int() truncation (losses.py:209)
+      iy = iy < 0 ? iy + h : iy;                 // python negative indexing
+      ix = ix < 0 ? ix + w : ix;
+      iy = min(max(iy, 0), h - 1);
+      ix = min(max(ix, 0), w - 1);
+      const float* f = fl + (((size_t)b * h + iy) * w + ix) * 2;
+      const float rx = sub_rn(dx_, add_rn(sx_, f[0])), ry = sub_rn(dy_, add_rn(sy_, f[1]));
+      e[dir] = __fsqrt_rn(add_rn(mul_rn(rx, rx), mul_rn(ry, ry)));
+    }
+    tot = add_rn(tot, fminf(e[0], e[1]));
+  }
+  err[b] = div_rn(tot, (float)P);
+}
+
+}  // namespace dmh
+
+using namespace dmh;
+
+extern "C" int dmh_homography_to_flow(const float* H, float* flow, int B, int h, int w, int divide, float start_x,
+                                      float start_y, const float* start, void* stream) {
+  DMH_REQUIRE(H && flow, "homography_to_flow: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0 && divide >= 1, "homography_to_flow: bad size");
+  DMH_REQUIRE(h % divide == 0 && w % divide == 0, "homography_to_flow: h,w must be divisible by divide");
+  h2flow_fwd_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(H, flow, B, h, w, divide,
+                                                                                         start_x, start_y, start);
+  return launched("h2flow_fwd_kernel");
+}
+
+extern "C" int dmh_homography_to_flow_backward(const float* H, const float* grad_flow, float* grad_H, int B, int h,
+                                               int w, int divide, float start_x, float start_y, const float* start,
+                                               void* stream) {
+  DMH_REQUIRE(H && grad_flow && grad_H, "homography_to_flow_backward: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0 && divide >= 1, "homography_to_flow_backward: bad size");
+  DMH_REQUIRE(h % divide == 0 && w % divide == 0, "homography_to_flow_backward: h,w must be divisible by divide");
+  DMH_REQUIRE(B <= 65535 && divide * divide <= 65535, "homography_to_flow_backward: B or divide^2 > 65535");
+  const long long npx = (long long)(h / divide) * (w / divide);
+  long long chunks = (npx + kThreads * 8 - 1) / (kThreads * 8);
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, (unsigned)(divide * divide), (unsigned)B);
+  h2flow_bwd_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(H, grad_flow, grad_H, B, h, w, divide, start_x, start_y,
+                                                              start);
+  return launched("h2flow_bwd_kernel");
+}
+
+extern "C" int dmh_homography_to_flow_f64(const double* H, float* out, int B, int h, int w, double eps,
+                                          int channels_last, int as_mapping, void* stream) {
+  DMH_REQUIRE(H && out, "homography_to_flow_f64: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "homography_to_flow_f64: bad size");
+  h2flow_f64_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(H, out, B, h, w, eps,
+                                                                                         channels_last, as_mapping);
+  return launched("h2flow_f64_kernel");
+}
+
+extern "C" int dmh_basis_combine(const float* basis, const float* weight, float* flow, int B, int h, int w,
+                                 void* stream) {
+  DMH_REQUIRE(basis && weight && flow, "basis_combine: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "basis_combine: bad size");
+  const long long plane = (long long)h * w;
+  const unsigned bx = (unsigned)((plane + kThreads - 1) / kThreads);
+  // enough CTAs for a few waves, but as many samples per CTA as possible (basis reuse)
+  int by = (int)((4LL * kNumSMs * 8 + bx - 1) / bx);
+  by = by < 1 ? 1 : (by > B ? B : by);
+  const int b_per_block = (B + by - 1) / by;
+  by = (B + b_per_block - 1) / b_per_block;
+  basis_combine_kernel<<<dim3(bx, (unsigned)by), kThreads, 0, as_stream(stream)>>>(basis, weight, flow, B, h, w,
+                                                                                   b_per_block);
+  return launched("basis_combine_kernel");
+}
+
+extern "C" int dmh_basis_combine_backward(const float* basis, const float* grad_flow, float* grad_weight, int B, int h,
+                                          int w, void* stream) {
+  DMH_REQUIRE(basis && grad_flow && grad_weight, "basis_combine_backward: null pointer");
+  DMH_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0, "basis_combine_backward: bad size");
+  const long long plane = (long long)h * w;
+  long long chunks = (plane + kThreads * 8 - 1) / (kThreads * 8);
+  basis_combine_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)B), kThreads, 0, as_stream(stream)>>>(
+      basis, grad_flow, grad_weight, B, h, w);
+  return launched("basis_combine_bwd_kernel");
+}
+
+extern "C" int dmh_border_mask(const float* flow, uint8_t* mask_u8, float* mask_f32, int B, int h, int w,
+                               void* stream) {
+  DMH_REQUIRE(flow && (mask_u8 || mask_f32), "border_mask: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "border_mask: bad size");
+  border_mask_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(flow, mask_u8, mask_f32, B,
+                                                                                          h, w);
+  return launched("border_mask_kernel");
+}
+
+extern "C" int dmh_zero_border_mask(const float* image, uint8_t* mask, int B, int h, int w, float eps, void* stream) {
+  DMH_REQUIRE(image && mask, "zero_border_mask: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "zero_border_mask: bad size");
+  zero_border_mask_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(image, mask, B, h, w,
+                                                                                               eps);
+  return launched("zero_border_mask_kernel");
+}
+
+extern "C" int dmh_l1_sum(const float* a, const float* b, int64_t n, double* acc, void* stream) {
+  DMH_REQUIRE(a && b && acc, "l1_sum: null pointer");
+  DMH_REQUIRE(n > 0, "l1_sum: n must be positive");
+  l1_sum_kernel<<<blocks_for(n, kThreads * 4), kThreads, 0, as_stream(stream)>>>(a, b, n, acc);
+  return launched("l1_sum_kernel");
+}
+
+extern "C" int dmh_l1_backward(const float* a, const float* b, int64_t n, const float* g, float scale, float* ga,
+                               float* gb, void* stream) {
+  DMH_REQUIRE(a && b && (ga || gb), "l1_backward: null pointer");
+  DMH_REQUIRE(n > 0, "l1_backward: n must be positive");
+  l1_bwd_kernel<<<blocks_for(n), kThreads, 0, as_stream(stream)>>>(a, b, n, g, scale, ga, gb);
+  return launched("l1_bwd_kernel");
+}
+
+extern "C" int dmh_loss_finish(const double* const* acc, const float* const* sample_weight, int n_acc, int B,
+                               float scale, float* loss, void* stream) {
+  DMH_REQUIRE(acc && loss, "loss_finish: null pointer");
+  DMH_REQUIRE(n_acc > 0 && n_acc <= 8 && B > 0, "loss_finish: n_acc must be in 1..8, B positive");
+  FinishArgs args;
+  for (int i = 0; i < 8; ++i) {
+    args.acc[i] = (i < n_acc) ? acc[i] : nullptr;
+    args.sw[i] = (i < n_acc && sample_weight) ? sample_weight[i] : nullptr;
+    if (i < n_acc) DMH_REQUIRE(acc[i] != nullptr, "loss_finish: acc[%d] is null", i);
+  }
+  loss_finish_kernel<<<1, kThreads, 0, as_stream(stream)>>>(args, n_acc, B, scale, loss);
+  return launched("loss_finish_kernel");
+}
+
+extern "C" int dmh_scale_inplace(float* x, int64_t n, const float* g, void* stream) {
+  DMH_REQUIRE(x && g, "scale_inplace: null pointer");
+  DMH_REQUIRE(n > 0, "scale_inplace: n must be positive");
+  scale_inplace_kernel<<<blocks_for(n), kThreads, 0, as_stream(stream)>>>(x, n, g);
+  return launched("scale_inplace_kernel");
+}
+
+extern "C" int dmh_flow_to_rgb(const float* flow, float* rgb, int B, int h, int w, float max_flow,
+                               int in_channels_last, int out_channels_last, void* stream) {
+  DMH_REQUIRE(flow && rgb, "flow_to_rgb: null pointer");
+  DMH_REQUIRE(B > 0 && h > 0 && w > 0, "flow_to_rgb: bad size");
+  DMH_REQUIRE(max_flow > 0.f, "flow_to_rgb: max_flow must be positive");
+  flow_to_rgb_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(
+      flow, rgb, B, h, w, max_flow, in_channels_last, out_channels_last);
+  return launched("flow_to_rgb_kernel");
+}
+
+extern "C" int dmh_eval_point_error(const float* pts, const float* flow_f, const float* flow_b, float* err, int B,
+                                    int P, int h, int w, void* stream) {
+  DMH_REQUIRE(pts && flow_f && flow_b && err, "eval_point_error: null pointer");
+  DMH_REQUIRE(B > 0 && P > 0 && h > 0 && w > 0, "eval_point_error: bad size");
+  eval_point_error_kernel<<<(B + 63) / 64, 64, 0, as_stream(stream)>>>(pts, flow_f, flow_b, err, B, P, h, w);
+  return launched("eval_point_error_kernel");
+}

@@ -1,0 +1,488 @@
+// Fused flow-generate + bilinear-sample + validity-mask + masked-L1 (+ gradients) kernel.
+//
+// Replaces, per output pixel, the reference's chain
+//   get_grid -> get_flow / basis combine -> get_warp_flow/transformer (or warp / flow_warp)
+//   -> create_border_mask -> LossL1(mask*a, mask*b)            (and its autograd backward)
+// HEM/model/utils.py:400-553, HEM/utils_operations/pixel_wise_mapping.py:55-113,
+// HEM/utils_operations/flow_and_mapping_operations.py:40-71, HEM/loss/losses.py:10-17,142-146,
+// DGM/denoising_diffusion_models/classifier_free_guidance.py:784-806.
+//
+// Layout: one CTA = 64x8 output pixels of one sample (256 threads, a warp owns one output
+// row: lanes are consecutive pixels, so source taps of a warp fall on 1-2 consecutive
+// 128-byte lines per tap row, target / output / mask accesses are fully coalesced and the
+// scatter of the backward lands on consecutive addresses that the LSU folds into
+// per-sector reductions).  Per-sample reductions (loss, dL/dH, dL/dw) go warp shuffle ->
+// shared memory -> one atomic per CTA.
+#include "dmh_common.cuh"
+
+namespace dmh {
+
+constexpr int TW = 64;   // tile width  (2 pixels per thread, 32 apart)
+constexpr int TH = 8;    // tile height (one row per warp)
+constexpr int NPX = 2;
+constexpr int NT = 256;
+constexpr int kMaxBatch = 4;
+
+enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
+
+struct WarpBatch {
+  dmh_warp_desc d[kMaxBatch];
+};
+
+struct Taps {
+  int ia, ib, ic, id;      // offsets inside one source plane: (y0,x0) (y1,x0) (y0,x1) (y1,x1)
+  float wa, wb, wc, wd;    // bilinear weights in the same order
+  float ax0, ax1, ay0, ay1;  // S1: x-x0f, x1f-x, y-y0f, y1f-y.  S2/S3: w, e, n, s
+  float gate_x, gate_y;    // d(sample coord)/d(cx): 0 where a clamp is active
+  bool va, vb, vc, vd;     // tap contributes (S2 zeros padding)
+};
+
+template <int SAMPLER>
+__device__ __forceinline__ void make_taps(float cx, float cy, int Hs, int Ws, Taps& t, int& x0o, int& y0o,
+                                          int& x1o, int& y1o) {
+  t.gate_x = 1.f;
+  t.gate_y = 1.f;
+  t.va = t.vb = t.vc = t.vd = true;
+  if (SAMPLER == DMH_S1 || SAMPLER == DMH_S1B) {
+    if (SAMPLER == DMH_S1B) {
+      // torch.clamp(coord, 0, size-1) before sampling (HEM/model/utils.py:108-109)
+      const float mx = (float)(Ws - 1), my = (float)(Hs - 1);
+      if (cx < 0.f || cx > mx) t.gate_x = 0.f;
+      if (cy < 0.f || cy > my) t.gate_y = 0.f;
+      cx = fminf(fmaxf(cx, 0.f), mx);
+      cy = fminf(fmaxf(cy, 0.f), my);
+    }
+    // floor -> int32 -> +1 -> clamp (utils.py:463-471); keep the cast in range
+    const float fxl = fminf(fmaxf(floorf(cx), -1.0e9f), 1.0e9f);
+    const float fyl = fminf(fmaxf(floorf(cy), -1.0e9f), 1.0e9f);
+    int x0 = (int)fxl, y0 = (int)fyl;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = min(max(x0, 0), Ws - 1);
+    x1 = min(max(x1, 0), Ws - 1);
+    y0 = min(max(y0, 0), Hs - 1);
+    y1 = min(max(y1, 0), Hs - 1);
+    const float x0f = (float)x0, x1f = (float)x1, y0f = (float)y0, y1f = (float)y1;
+    t.ax1 = sub_rn(x1f, cx);
+    t.ax0 = sub_rn(cx, x0f);
+    t.ay1 = sub_rn(y1f, cy);
+    t.ay0 = sub_rn(cy, y0f);
+    t.wa = mul_rn(t.ax1, t.ay1);
+    t.wb = mul_rn(t.ax1, t.ay0);
+    t.wc = mul_rn(t.ax0, t.ay1);
+    t.wd = mul_rn(t.ax0, t.ay0);
+    t.ia = y0 * Ws + x0;
+    t.ib = y1 * Ws + x0;
+    t.ic = y0 * Ws + x1;
+    t.id = y1 * Ws + x1;
+    x0o = x0; y0o = y0; x1o = x1; y1o = y1;
+  } else {
+    // normalise to [-1,1] exactly as the reference does, then ATen's align_corners=True
+    // un-normalisation (pixel_wise_mapping.py:79-80 / data_loader.py:80-81; App. A.4)
+    const float dw = (SAMPLER == DMH_S2_ZEROS) ? (float)max(Ws - 1, 1) : (float)(Ws - 1);
+    const float dh = (SAMPLER == DMH_S2_ZEROS) ? (float)max(Hs - 1, 1) : (float)(Hs - 1);
+    const float nx = sub_rn(div_rn(mul_rn(2.0f, cx), dw), 1.0f);
+    const float ny = sub_rn(div_rn(mul_rn(2.0f, cy), dh), 1.0f);
+    const float sxf = (float)(Ws - 1) * 0.5f, syf = (float)(Hs - 1) * 0.5f;
+    float ix = mul_rn(add_rn(nx, 1.0f), sxf);
+    float iy = mul_rn(add_rn(ny, 1.0f), syf);
+    t.gate_x = mul_rn(sxf, div_rn(2.0f, dw));
+    t.gate_y = mul_rn(syf, div_rn(2.0f, dh));
+    if (SAMPLER == DMH_S3_BORDER) {
+      const float mx = (float)(Ws - 1), my = (float)(Hs - 1);
+      if (!(ix > 0.f && ix < mx)) t.gate_x = 0.f;
+      if (!(iy > 0.f && iy < my)) t.gate_y = 0.f;
+      ix = fminf(fmaxf(ix, 0.f), mx);
+      iy = fminf(fmaxf(iy, 0.f), my);
+    }
+    const float fxl = fminf(fmaxf(floorf(ix), -1.0e9f), 1.0e9f);
+    const float fyl = fminf(fmaxf(floorf(iy), -1.0e9f), 1.0e9f);
+    const int x0 = (int)fxl, y0 = (int)fyl, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx = sub_rn(ix, fxl), wy = sub_rn(iy, fyl);  // dist to west / north
+    const float ex = sub_rn(1.0f, wx), sy = sub_rn(1.0f, wy);
+    t.ax0 = wx; t.ax1 = ex; t.ay0 = wy; t.ay1 = sy;
+    t.wa = mul_rn(sy, ex);  // nw
+    t.wc = mul_rn(sy, wx);  // ne
+    t.wb = mul_rn(wy, ex);  // sw
+    t.wd = mul_rn(wy, wx);  // se
+    const bool x0in = (x0 >= 0 && x0 <= Ws - 1), x1in = (x1 >= 0 && x1 <= Ws - 1);
+    const bool y0in = (y0 >= 0 && y0 <= Hs - 1), y1in = (y1 >= 0 && y1 <= Hs - 1);
+    t.va = x0in && y0in; t.vb = x0in && y1in; t.vc = x1in && y0in; t.vd = x1in && y1in;
+    const int x0c = min(max(x0, 0), Ws - 1), x1c = min(max(x1, 0), Ws - 1);
+    const int y0c = min(max(y0, 0), Hs - 1), y1c = min(max(y1, 0), Hs - 1);
+    t.ia = y0c * Ws + x0c; t.ib = y1c * Ws + x0c; t.ic = y0c * Ws + x1c; t.id = y1c * Ws + x1c;
+    x0o = x0c; y0o = y0c; x1o = x1c; y1o = y1c;
+  }
+}
+
+template <int SAMPLER>
+__device__ __forceinline__ float blend(const Taps& t, float Ia, float Ib, float Ic, float Id) {
+  if (SAMPLER == DMH_S1 || SAMPLER == DMH_S1B) {
+    // output = wa*Ia + wb*Ib + wc*Ic + wd*Id, left to right, no FMA (utils.py:523)
+    return add_rn(add_rn(add_rn(mul_rn(t.wa, Ia), mul_rn(t.wb, Ib)), mul_rn(t.wc, Ic)), mul_rn(t.wd, Id));
+  } else {
+    // ATen: nw*nw_val + ne*ne_val + sw*sw_val + se*se_val
+    return add_rn(add_rn(add_rn(mul_rn(Ia, t.wa), mul_rn(Ic, t.wc)), mul_rn(Ib, t.wb)), mul_rn(Id, t.wd));
+  }
+}
+
+template <int SAMPLER, int PARAM, int PASS, int CT>
+__global__ void __launch_bounds__(NT) warp_kernel(const __grid_constant__ WarpBatch batch) {
+  const dmh_warp_desc& d = batch.d[blockIdx.y];
+  const int C = CT ? CT : d.C;
+  const int h = d.h, w = d.w, Hs = d.Hs, Ws = d.Ws;
+  const int tiles_x = (w + TW - 1) / TW, tiles_y = (h + TH - 1) / TH;
+  int t = blockIdx.x;
+  const int b = t / (tiles_x * tiles_y);
+  t -= b * tiles_x * tiles_y;
+  const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int y = tyi * TH + wrp;
+  const bool row_live = y < h;
+  constexpr bool kGrad = (PASS != PASS_FWD);
+  constexpr bool kOut = (PASS != PASS_BWD);
+
+  const size_t plane_o = (size_t)h * w;
+  const size_t plane_s = (size_t)Hs * Ws;
+
+  float sx = d.start_x, sy = d.start_y;
+  if (d.start) {
+    sx = __ldg(d.start + 2 * b);
+    sy = __ldg(d.start + 2 * b + 1);
+  }
+  const float gy = add_rn((float)y, sy);
+
+  // per-sample parameters
+  float hm[9];
+  float bw[8];
+  if (PARAM == DMH_PARAM_HOMOGRAPHY && d.divide == 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hm[k] = __ldg(d.param + (size_t)b * 9 + k);
+  }
+  if (PARAM == DMH_PARAM_BASIS8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bw[k] = __ldg(d.param + (size_t)b * 8 + k);
+  }
+
+  const bool want_mask = (d.valid != nullptr) || d.use_border_mask;
+  const bool has_loss = (d.loss_form != DMH_LOSS_NONE) && (d.target != nullptr);
+
+  float gscale = 0.f;
+  if (kGrad && has_loss) {
+    gscale = d.grad_loss_scale;
+    if (PASS == PASS_BWD && d.grad_loss) gscale *= __ldg(d.grad_loss);
+    if (d.sample_weight) gscale *= __ldg(d.sample_weight + b);
+  }
+
+  float lsum = 0.f;
+  float gacc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gacc[k] = 0.f;
+
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    const int x = txi * TW + lane + 32 * i;
+    const bool live = row_live && (x < w);
+    if (!live) continue;
+    const size_t po = (size_t)y * w + x;  // offset in an output plane
+    const float gx = add_rn((float)x, sx);
+
+    // ---- sampling coordinate ------------------------------------------------------
+    float fx = 0.f, fy = 0.f, cx, cy;
+    float qX = 0.f, qY = 0.f, qT = 1.f;  // homography numerators / denominator (for grads)
+    float hx = gx, hy = gy;              // grid point the homography is applied to
+    int cell = 0;
+    if (PARAM == DMH_PARAM_FLOW) {
+      fx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
+      fy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
+      cx = add_rn(gx, fx);
+      cy = add_rn(gy, fy);
+    } else if (PARAM == DMH_PARAM_COORDS) {
+      cx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
+      cy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
+      fx = sub_rn(cx, gx);
+      fy = sub_rn(cy, gy);
+    } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+      if (d.divide != 1) {
+        const int dv = d.divide;
+        cell = min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1);
+        const float* Hp = d.param + ((size_t)b * dv * dv + cell) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) hm[k] = __ldg(Hp + k);
+      }
+      // WarpImages (S1B) applies H to the un-offset grid and adds `start` afterwards
+      // (HEM/model/utils.py:171-192); get_flow applies it to grid + start (utils.py:400-440).
+      hx = (SAMPLER == DMH_S1B) ? (float)x : gx;
+      hy = (SAMPLER == DMH_S1B) ? (float)y : gy;
+      // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
+      qX = add_rn(add_rn(mul_rn(hm[0], hx), mul_rn(hm[1], hy)), hm[2]);
+      qY = add_rn(add_rn(mul_rn(hm[3], hx), mul_rn(hm[4], hy)), hm[5]);
+      qT = add_rn(add_rn(mul_rn(hm[6], hx), mul_rn(hm[7], hy)), hm[8]);
+      if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
+      fx = sub_rn(div_rn(qX, qT), hx);
+      fy = sub_rn(div_rn(qY, qT), hy);
+      cx = add_rn(gx, fx);
+      cy = add_rn(gy, fy);
+    } else {  // BASIS8: acc = b0*w0; acc += bk*wk, products rounded separately (A12)
+      const float* bp = d.basis + po;
+      fx = mul_rn(__ldg(bp), bw[0]);
+      fy = mul_rn(__ldg(bp + plane_o), bw[0]);
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        fx = add_rn(fx, mul_rn(__ldg(bp + (size_t)(2 * k) * plane_o), bw[k]));
+        fy = add_rn(fy, mul_rn(__ldg(bp + (size_t)(2 * k + 1) * plane_o), bw[k]));
+      }
+      cx = add_rn(gx, fx);
+      cy = add_rn(gy, fy);
+    }
+
+    // ---- M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h ----------
+    float m = 1.f;
+    bool m1 = true;
+    if (want_mask) {
+      const float mx = (PARAM == DMH_PARAM_COORDS) ? cx : add_rn(fx, (float)x);
+      const float my = (PARAM == DMH_PARAM_COORDS) ? cy : add_rn(fy, (float)y);
+      m1 = (mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h);
+      if (kOut && d.valid) d.valid[(size_t)b * plane_o + po] = m1 ? 1 : 0;
+      if (d.use_border_mask) m = m1 ? 1.f : 0.f;
+    }
+    float soft = 1.f;
+    if (d.soft_mask) {
+      soft = __ldg(d.soft_mask + (size_t)b * plane_o + po);
+      m = mul_rn(m, soft);
+    }
+    if (kOut && d.flow_out) {
+      d.flow_out[((size_t)b * 2) * plane_o + po] = fx;
+      d.flow_out[((size_t)b * 2 + 1) * plane_o + po] = fy;
+    }
+
+    // ---- taps ------------------------------------------------------------------------------
+    Taps tp;
+    int x0, y0, x1, y1;
+    make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
+    if (kOut && d.indices) {
+      const size_t n = (size_t)d.B * plane_o, o = (size_t)b * plane_o + po;
+      d.indices[o] = x0;
+      d.indices[n + o] = y0;
+      d.indices[2 * n + o] = x1;
+      d.indices[3 * n + o] = y1;
+    }
+
+    float gcx = 0.f, gcy = 0.f, gmask = 0.f;
+#pragma unroll(CT ? CT : 1)
+    for (int c = 0; c < C; ++c) {
+      const float* sp = d.src + ((size_t)b * C + c) * plane_s;
+      const size_t oo = ((size_t)b * C + c) * plane_o + po;
+      float Ia = __ldg(sp + tp.ia), Ib = __ldg(sp + tp.ib), Ic = __ldg(sp + tp.ic), Id = __ldg(sp + tp.id);
+      if (SAMPLER == DMH_S2_ZEROS) {
+        Ia = tp.va ? Ia : 0.f; Ib = tp.vb ? Ib : 0.f; Ic = tp.vc ? Ic : 0.f; Id = tp.vd ? Id : 0.f;
+      }
+      const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
+      if (kOut && d.out) d.out[oo] = wv;
+      float go = 0.f;  // dL/d(out)
+      if (kGrad && PASS == PASS_BWD && d.grad_out) go = __ldg(d.grad_out + oo);
+      if (has_loss) {
+        const float tv = __ldg(d.target + oo);
+        float s, gm_c;
+        if (d.loss_form == DMH_LOSS_MASKED_DIFF) {
+          const float u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));
+          if (kOut) lsum += fabsf(u);
+          s = sign_of(u);                 // d|u|/d(tv) = m*s ; d/d(wv) = -m*s ; d/dm = s*(tv-wv)
+          gm_c = s * (tv - wv);
+          s = m * s;
+        } else {
+          const float u = sub_rn(wv, tv);
+          if (kOut) lsum += m * fabsf(u);
+          gm_c = fabsf(u);
+          s = -m * sign_of(u);            // d/d(tv) = -m*sign ; d/d(wv) = +m*sign
+        }
+        if (kGrad) {
+          const float gt = gscale * s;
+          go -= gt;
+          if (d.grad_target && gt != 0.f) red_add(d.grad_target + oo, gt);
+          gmask += gscale * gm_c;
+        }
+      }
+      if (kGrad) {
+        if (d.grad_src && go != 0.f) {
+          float* gp = d.grad_src + ((size_t)b * C + c) * plane_s;
+          if (SAMPLER != DMH_S2_ZEROS || tp.va) red_add(gp + tp.ia, tp.wa * go);
+          if (SAMPLER != DMH_S2_ZEROS || tp.vb) red_add(gp + tp.ib, tp.wb * go);
+          if (SAMPLER != DMH_S2_ZEROS || tp.vc) red_add(gp + tp.ic, tp.wc * go);
+          if (SAMPLER != DMH_S2_ZEROS || tp.vd) red_add(gp + tp.id, tp.wd * go);
+        }
+        // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
+        gcx += go * (tp.ay1 * (Ic - Ia) + tp.ay0 * (Id - Ib));
+        gcy += go * (tp.ax1 * (Ib - Ia) + tp.ax0 * (Id - Ic));
+      }
+    }
+
+    if (kGrad) {
+      gcx *= tp.gate_x;
+      gcy *= tp.gate_y;
+      if (d.grad_soft_mask) d.grad_soft_mask[(size_t)b * plane_o + po] = (d.use_border_mask && !m1) ? 0.f : gmask;
+      if (d.grad_param) {
+        if (PARAM == DMH_PARAM_FLOW || PARAM == DMH_PARAM_COORDS) {
+          d.grad_param[((size_t)b * 2) * plane_o + po] = gcx;
+          d.grad_param[((size_t)b * 2 + 1) * plane_o + po] = gcy;
+        } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+          // flow = q/T' - g  =>  dX = g/T', dT = -(gcx*X + gcy*Y)/T'^2
+          const float rT = 1.f / qT;
+          const float gX = gcx * rT, gY = gcy * rT;
+          const float gT = -(gcx * qX + gcy * qY) * rT * rT;
+          if (d.divide == 1) {
+            gacc[0] += gX * hx; gacc[1] += gX * hy; gacc[2] += gX;
+            gacc[3] += gY * hx; gacc[4] += gY * hy; gacc[5] += gY;
+            gacc[6] += gT * hx; gacc[7] += gT * hy; gacc[8] += gT;
+          } else {  // mesh of homographies: rare path, straight to global
+            float* gp = d.grad_param + ((size_t)b * d.divide * d.divide + cell) * 9;
+            red_add(gp + 0, gX * hx); red_add(gp + 1, gX * hy); red_add(gp + 2, gX);
+            red_add(gp + 3, gY * hx); red_add(gp + 4, gY * hy); red_add(gp + 5, gY);
+            red_add(gp + 6, gT * hx); red_add(gp + 7, gT * hy); red_add(gp + 8, gT);
+          }
+        } else {
+          const float* bp = d.basis + po;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            gacc[k] += gcx * __ldg(bp + (size_t)(2 * k) * plane_o) + gcy * __ldg(bp + (size_t)(2 * k + 1) * plane_o);
+        }
+      }
+    }
+  }
+
+  // ---- per-CTA reductions: warp shuffle -> shared -> one atomic per value ---------------------
+  __shared__ float red[NT / 32][10];
+  const bool reduce_param = kGrad && d.grad_param &&
+                            ((PARAM == DMH_PARAM_HOMOGRAPHY && d.divide == 1) || PARAM == DMH_PARAM_BASIS8);
+  const bool reduce_loss = kOut && has_loss && d.loss_acc;
+  if (!reduce_param && !reduce_loss) return;
+  if (reduce_loss) {
+    const float v = warp_sum(lsum);
+    if (lane == 0) red[wrp][9] = v;
+  }
+  if (reduce_param) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float v = warp_sum(gacc[k]);
+      if (lane == 0) red[wrp][k] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    const int k = threadIdx.x;
+    if ((k == 9 && reduce_loss) || (k < 9 && reduce_param)) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT / 32; ++q) v += red[q][k];
+      if (k == 9) {
+        atomicAdd(d.loss_acc + b, (double)v);
+      } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+        red_add(d.grad_param + (size_t)b * 9 + k, v);
+      } else if (k < 8) {
+        red_add(d.grad_param + (size_t)b * 8 + k, v);
+      }
+    }
+  }
+}
+
+// ---- host dispatch -------------------------------------------------------------------------
+
+template <int SAMPLER, int PARAM, int PASS, int CT>
+static int launch(const WarpBatch& batch, int n, cudaStream_t stream) {
+  const dmh_warp_desc& d = batch.d[0];
+  const long long tiles = (long long)((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH) * d.B;
+  if (tiles > 2147483647LL) return fail(DMH_EUNSUPPORTED, "warp: too many tiles (%lld)", tiles);
+  dim3 grid((unsigned)tiles, (unsigned)n, 1);
+  warp_kernel<SAMPLER, PARAM, PASS, CT><<<grid, NT, 0, stream>>>(batch);
+  return launched("warp_kernel");
+}
+
+template <int SAMPLER, int PARAM, int PASS>
+static int launch_c(const WarpBatch& batch, int n, cudaStream_t stream) {
+  const int C = batch.d[0].C;
+  if (SAMPLER == DMH_S1 || SAMPLER == DMH_S3_BORDER) {
+    if (C == 1) return launch<SAMPLER, PARAM, PASS, 1>(batch, n, stream);
+    if (C == 3) return launch<SAMPLER, PARAM, PASS, 3>(batch, n, stream);
+  }
+  return launch<SAMPLER, PARAM, PASS, 0>(batch, n, stream);
+}
+
+template <int SAMPLER, int PASS>
+static int launch_p(const WarpBatch& batch, int n, cudaStream_t stream) {
+  switch (batch.d[0].param_kind) {
+    case DMH_PARAM_FLOW: return launch_c<SAMPLER, DMH_PARAM_FLOW, PASS>(batch, n, stream);
+    case DMH_PARAM_COORDS: return launch_c<SAMPLER, DMH_PARAM_COORDS, PASS>(batch, n, stream);
+    case DMH_PARAM_HOMOGRAPHY: return launch_c<SAMPLER, DMH_PARAM_HOMOGRAPHY, PASS>(batch, n, stream);
+    case DMH_PARAM_BASIS8: return launch_c<SAMPLER, DMH_PARAM_BASIS8, PASS>(batch, n, stream);
+  }
+  return fail(DMH_EINVAL, "warp: bad param_kind %d", batch.d[0].param_kind);
+}
+
+template <int PASS>
+static int launch_s(const WarpBatch& batch, int n, cudaStream_t stream) {
+  switch (batch.d[0].sampler) {
+    case DMH_S1: return launch_p<DMH_S1, PASS>(batch, n, stream);
+    case DMH_S1B: return launch_p<DMH_S1B, PASS>(batch, n, stream);
+    case DMH_S2_ZEROS: return launch_p<DMH_S2_ZEROS, PASS>(batch, n, stream);
+    case DMH_S3_BORDER: return launch_p<DMH_S3_BORDER, PASS>(batch, n, stream);
+  }
+  return fail(DMH_EINVAL, "warp: bad sampler %d", batch.d[0].sampler);
+}
+
+static int validate(const dmh_warp_desc& d, bool backward) {
+  DMH_REQUIRE(d.struct_size == sizeof(dmh_warp_desc), "warp: struct_size %u != %zu (ABI mismatch)", d.struct_size,
+              sizeof(dmh_warp_desc));
+  DMH_REQUIRE(d.B > 0 && d.C > 0 && d.Hs > 0 && d.Ws > 0 && d.h > 0 && d.w > 0, "warp: non-positive size");
+  DMH_REQUIRE((long long)d.Hs * d.Ws < 2147483647LL && (long long)d.h * d.w < 2147483647LL, "warp: plane too large");
+  DMH_REQUIRE(d.src != nullptr, "warp: src is null");
+  DMH_REQUIRE(d.param != nullptr, "warp: param is null");
+  DMH_REQUIRE(d.param_kind != DMH_PARAM_BASIS8 || d.basis != nullptr, "warp: BASIS8 needs basis");
+  DMH_REQUIRE(d.loss_form >= DMH_LOSS_NONE && d.loss_form <= DMH_LOSS_DIFF_MASKED, "warp: bad loss_form");
+  if (d.param_kind == DMH_PARAM_HOMOGRAPHY) {
+    DMH_REQUIRE(d.divide >= 1, "warp: divide must be >= 1");
+    DMH_REQUIRE(d.h % d.divide == 0 && d.w % d.divide == 0, "warp: h,w must be divisible by divide");
+  }
+  if (d.loss_form != DMH_LOSS_NONE) DMH_REQUIRE(d.target != nullptr, "warp: loss needs target");
+  if (backward)
+    DMH_REQUIRE(d.grad_out != nullptr || d.loss_form != DMH_LOSS_NONE, "warp backward: no upstream gradient");
+  return DMH_OK;
+}
+
+static bool same_config(const dmh_warp_desc& a, const dmh_warp_desc& b) {
+  return a.sampler == b.sampler && a.param_kind == b.param_kind && a.B == b.B && a.C == b.C && a.Hs == b.Hs &&
+         a.Ws == b.Ws && a.h == b.h && a.w == b.w;
+}
+
+static int run(const dmh_warp_desc* descs, int n, void* stream, bool backward) {
+  DMH_REQUIRE(descs != nullptr && n > 0, "warp: no descriptors");
+  for (int i = 0; i < n; ++i) {
+    int rc = validate(descs[i], backward);
+    if (rc) return rc;
+  }
+  int i = 0;
+  while (i < n) {
+    WarpBatch batch;
+    int m = 0;
+    const bool fused0 = !backward && descs[i].compute_grads;
+    while (i + m < n && m < kMaxBatch && same_config(descs[i], descs[i + m]) &&
+           (!backward && descs[i + m].compute_grads) == fused0) {
+      batch.d[m] = descs[i + m];
+      ++m;
+    }
+    for (int k = m; k < kMaxBatch; ++k) batch.d[k] = batch.d[0];
+    int rc = backward ? launch_s<PASS_BWD>(batch, m, as_stream(stream))
+                      : (fused0 ? launch_s<PASS_FUSED>(batch, m, as_stream(stream))
+                                : launch_s<PASS_FWD>(batch, m, as_stream(stream)));
+    if (rc) return rc;
+    i += m;
+  }
+  return DMH_OK;
+}
+
+}  // namespace dmh
+
+extern "C" int dmh_warp_forward(const dmh_warp_desc* descs, int n, void* stream) {
+  return dmh::run(descs, n, stream, false);
+}
+extern "C" int dmh_warp_backward(const dmh_warp_desc* descs, int n, void* stream) {
+  return dmh::run(descs, n, stream, true);
+}

@@ -1,0 +1,649 @@
+"""torch-facing operators over libdmhomo (C ABI in include/dmhomo.h).
+
+PyTorch is only plumbing here: it owns device memory, streams and the autograd graph.
+Every op enqueues hand-written sm_100a kernels on the caller's current stream through
+ctypes; there is no CPU path and no PyTorch re-implementation to fall back on.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import (LOSS_DIFF_MASKED, LOSS_MASKED_DIFF, LOSS_NONE, PARAM_BASIS8, PARAM_COORDS, PARAM_FLOW,
+                   PARAM_HOMOGRAPHY, S1, S1B, S2_ZEROS, S3_BORDER)
+
+__all__ = [
+    "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8",
+    "LOSS_NONE", "LOSS_MASKED_DIFF", "LOSS_DIFF_MASKED", "dlt4", "homography_to_flow", "homography_to_flow_f64",
+    "basis_combine", "basis_corner_offsets", "warp", "warp_loss", "WarpTerm", "border_mask", "zero_border_mask",
+    "l1_loss", "flow_to_rgb", "warp_perspective", "eval_point_error", "flow_to_homography_ls",
+]
+
+
+# ----------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------
+def _cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise L.DmhError("dmhomo_b200 ops take CUDA tensors only (there is no CPU fallback); got a "
+                             f"{t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise L.DmhError(f"dmhomo_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _start_args(start, B, dev):
+    """`start` of get_grid(): a number (added to x and y), an (sx, sy) pair, or a tensor
+    broadcastable to (B,2,1,1).  Returns (sx, sy, per_sample_tensor_or_None)."""
+    if torch.is_tensor(start):
+        s = _f32(start.to(dev)).reshape(-1)
+        if s.numel() == 1:
+            s = s.expand(2 * B)
+        elif s.numel() == 2:
+            s = s.repeat(B)
+        elif s.numel() != 2 * B:
+            raise ValueError(f"start tensor must broadcast to (B,2,1,1); got {tuple(start.shape)}")
+        return 0.0, 0.0, s.contiguous().view(B, 2)
+    if isinstance(start, (tuple, list)):
+        return float(start[0]), float(start[1]), None
+    return float(start), float(start), None
+
+
+def _desc(sampler, kind, src, param, h, w, **kw):
+    B, Cc, Hs, Ws = src.shape
+    d = L.WarpDesc()
+    d.struct_size = C.sizeof(L.WarpDesc)
+    d.sampler, d.param_kind = sampler, kind
+    d.loss_form = kw.get("loss_form", LOSS_NONE)
+    d.B, d.C, d.Hs, d.Ws, d.h, d.w = B, Cc, Hs, Ws, h, w
+    d.divide = kw.get("divide", 1)
+    d.use_border_mask = int(bool(kw.get("use_border_mask", False)))
+    d.compute_grads = int(bool(kw.get("compute_grads", False)))
+    d.start_x, d.start_y = kw.get("start_x", 0.0), kw.get("start_y", 0.0)
+    d.grad_loss_scale = kw.get("grad_loss_scale", 0.0)
+    d.src, d.param = _p(src), _p(param)
+    for name in ("basis", "start", "target", "soft_mask", "sample_weight", "grad_out", "grad_loss", "out", "valid",
+                 "flow_out", "indices", "loss_acc", "grad_src", "grad_target", "grad_param", "grad_soft_mask"):
+        setattr(d, name, _p(kw.get(name)))
+    return d
+
+
+def _run_warp(descs, dev, backward=False):
+    arr = (L.WarpDesc * len(descs))(*descs)
+    fn = L.lib().dmh_warp_backward if backward else L.lib().dmh_warp_forward
+    with torch.cuda.device(dev):
+        L.check(fn(arr, len(descs), _stream(dev)), "warp_backward" if backward else "warp_forward")
+
+
+def _param_shape_check(kind, param, B, h, w, divide):
+    if kind in (PARAM_FLOW, PARAM_COORDS):
+        if tuple(param.shape) != (B, 2, h, w):
+            raise ValueError(f"flow/coords must be (B,2,h,w)={(B, 2, h, w)}, got {tuple(param.shape)}")
+    elif kind == PARAM_HOMOGRAPHY:
+        if param.numel() != B * divide * divide * 9:
+            raise ValueError(f"homography must hold B*divide^2*9 values, got {tuple(param.shape)}")
+    elif kind == PARAM_BASIS8:
+        if param.numel() != B * 8:
+            raise ValueError(f"basis weights must hold B*8 values, got {tuple(param.shape)}")
+    else:
+        raise ValueError(f"bad param kind {kind}")
+
+
+# ----------------------------------------------------------------------------------------------
+# DLT (A1-A3)
+# ----------------------------------------------------------------------------------------------
+class _DLT4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, dst):
+        dev = _cuda(src, dst)
+        src_c, dst_c = _f32(src), _f32(dst)
+        N = src_c.numel() // 8
+        H = torch.empty(N, 3, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_dlt4_forward(_p(src_c), _p(dst_c), _p(H), N, _stream(dev)), "dlt4_forward")
+        ctx.save_for_backward(src_c, dst_c, H)
+        ctx.shapes = (src.shape, dst.shape)
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        src, dst, H = ctx.saved_tensors
+        dev = src.device
+        N = H.shape[0]
+        gH = _f32(gH)
+        g_dst = torch.empty_like(dst)
+        g_src = torch.empty_like(src) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_dlt4_backward(_p(src), _p(dst), _p(H), _p(gH), _p(g_dst), _p(g_src), N, _stream(dev)),
+                    "dlt4_backward")
+        return (g_src.view(ctx.shapes[0]) if g_src is not None else None), g_dst.view(ctx.shapes[1])
+
+
+def dlt4(src_pt, dst_pt):
+    """N independent 4-point DLT solves: (..,4,2),(..,4,2) -> (N,3,3), H[2,2] = 1.
+    Replaces DLT.forward('Axb') (HEM/model/utils.py:55-101)."""
+    if src_pt.numel() % 8 or src_pt.numel() != dst_pt.numel():
+        raise ValueError("dlt4: src/dst must hold N*4*2 values each")
+    return _DLT4.apply(src_pt, dst_pt)
+
+
+# ----------------------------------------------------------------------------------------------
+# homography -> flow (A5, A15)
+# ----------------------------------------------------------------------------------------------
+class _H2Flow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, h, w, divide, start):
+        dev = _cuda(H)
+        Hc = _f32(H)
+        B = Hc.numel() // (9 * divide * divide)
+        sx, sy, per = _start_args(start, B, dev)
+        flow = torch.empty(B, 2, h, w, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_homography_to_flow(_p(Hc), _p(flow), B, h, w, divide, sx, sy, _p(per), _stream(dev)),
+                    "homography_to_flow")
+        ctx.save_for_backward(Hc, per)
+        ctx.cfg = (B, h, w, divide, sx, sy, H.shape)
+        return flow
+
+    @staticmethod
+    def backward(ctx, gflow):
+        Hc, per = ctx.saved_tensors
+        B, h, w, divide, sx, sy, shape = ctx.cfg
+        dev = Hc.device
+        gflow = _f32(gflow)
+        gH = torch.zeros_like(Hc)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_homography_to_flow_backward(_p(Hc), _p(gflow), _p(gH), B, h, w, divide, sx, sy,
+                                                            _p(per), _stream(dev)), "homography_to_flow_backward")
+        return gH.view(shape), None, None, None, None
+
+
+def homography_to_flow(H, h, w, divide=1, start=0):
+    """get_flow() (HEM/model/utils.py:400-440): H (B,[divide^2,]3,3) -> flow (B,2,h,w), fp32 with the
+    reference's rounding order and epsilon rule.  `start` as in get_grid() (number, pair, or a
+    tensor broadcastable to (B,2,1,1))."""
+    return _H2Flow.apply(H, int(h), int(w), int(divide), start)
+
+
+def homography_to_flow_f64(H, h, w, eps=1e-6, channels_last=True, as_mapping=False):
+    """homo_to_flow()/get_flow_np() (ddpm.py:913-975; eps=1e-6) and
+    from_homography_to_pixel_wise_mapping() (flow_and_mapping_operations.py:454-484; eps=1e-8,
+    as_mapping=True): fp64 arithmetic, fp32 result.  H: (B,3,3) float64 CUDA tensor."""
+    dev = _cuda(H)
+    Hc = H.to(torch.float64).contiguous()
+    B = Hc.numel() // 9
+    shape = (B, h, w, 2) if channels_last else (B, 2, h, w)
+    out = torch.empty(shape, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_homography_to_flow_f64(_p(Hc), _p(out), B, h, w, float(eps), int(channels_last),
+                                                   int(as_mapping), _stream(dev)), "homography_to_flow_f64")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# basis flows (A12)
+# ----------------------------------------------------------------------------------------------
+class _BasisCombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, basis, weight, h, w):
+        dev = _cuda(basis, weight)
+        bc, wc = _f32(basis), _f32(weight)
+        B = wc.numel() // 8
+        flow = torch.empty(B, 2, h, w, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_combine(_p(bc), _p(wc), _p(flow), B, h, w, _stream(dev)), "basis_combine")
+        ctx.save_for_backward(bc)
+        ctx.cfg = (B, h, w, weight.shape)
+        return flow
+
+    @staticmethod
+    def backward(ctx, gflow):
+        (bc,) = ctx.saved_tensors
+        B, h, w, wshape = ctx.cfg
+        dev = bc.device
+        gflow = _f32(gflow)
+        gw = torch.zeros(B, 8, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_combine_backward(_p(bc), _p(gflow), _p(gw), B, h, w, _stream(dev)),
+                    "basis_combine_backward")
+        return None, gw.view(wshape), None, None
+
+
+def basis_combine(basis, weight, h, w):
+    """flow = sum_k w_k basis_k (HEM/model/net.py:808-815).  basis holds 8*2*h*w values laid out
+    (8,2,h,w) (== the reference's (1,8,2*h*w)); weight (B,8[,1]) -> (B,2,h,w)."""
+    if basis.numel() != 16 * h * w:
+        raise ValueError("basis must hold 8*2*h*w values")
+    return _BasisCombine.apply(basis, weight, int(h), int(w))
+
+
+class _BasisCorners(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, basis, weight, h, w):
+        dev = _cuda(basis, weight)
+        bc, wc = _f32(basis), _f32(weight)
+        B = wc.numel() // 8
+        off = torch.empty(B, 4, 2, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_corner_offsets(_p(bc), _p(wc), _p(off), B, h, w, _stream(dev)),
+                    "basis_corner_offsets")
+        ctx.save_for_backward(bc)
+        ctx.cfg = (B, h, w, weight.shape)
+        return off
+
+    @staticmethod
+    def backward(ctx, goff):
+        (bc,) = ctx.saved_tensors
+        B, h, w, wshape = ctx.cfg
+        dev = bc.device
+        goff = _f32(goff)
+        gw = torch.zeros(B, 8, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_corner_offsets_backward(_p(bc), _p(goff), _p(gw), B, h, w, _stream(dev)),
+                    "basis_corner_offsets_backward")
+        return None, gw.view(wshape), None, None
+
+
+def basis_corner_offsets(basis, weight, h, w):
+    """The basis flow sampled at the 4 image corners (TL,TR,BL,BR) as 4-point offsets (B,4,2)."""
+    if basis.numel() != 16 * h * w:
+        raise ValueError("basis must hold 8*2*h*w values")
+    return _BasisCorners.apply(basis, weight, int(h), int(w))
+
+
+# ----------------------------------------------------------------------------------------------
+# warp (A6-A9)
+# ----------------------------------------------------------------------------------------------
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, param, basis, cfg):
+        dev = _cuda(img, param, basis)
+        img_c, par_c, bas_c = _f32(img), _f32(param), _f32(basis)
+        B, Cc, Hs, Ws = img_c.shape
+        h, w = cfg["h"], cfg["w"]
+        _param_shape_check(cfg["kind"], par_c, B, h, w, cfg["divide"])
+        sx, sy, per = _start_args(cfg["start"], B, dev)
+        out = torch.empty(B, Cc, h, w, device=dev, dtype=torch.float32)
+        valid = torch.empty(B, h, w, device=dev, dtype=torch.uint8) if cfg["mask"] else None
+        flow = torch.empty(B, 2, h, w, device=dev, dtype=torch.float32) if cfg["flow"] else None
+        idx = torch.empty(4, B, h, w, device=dev, dtype=torch.int32) if cfg["indices"] else None
+        d = _desc(cfg["sampler"], cfg["kind"], img_c, par_c, h, w, basis=bas_c, start=per, start_x=sx, start_y=sy,
+                  divide=cfg["divide"], out=out, valid=valid, flow_out=flow, indices=idx)
+        _run_warp([d], dev)
+        ctx.save_for_backward(img_c, par_c, bas_c, per)
+        ctx.cfg = dict(cfg, sx=sx, sy=sy, pshape=param.shape)
+        extras = tuple(t for t in (valid, flow, idx) if t is not None)
+        ctx.mark_non_differentiable(*extras)
+        return (out,) + extras
+
+    @staticmethod
+    def backward(ctx, gout, *_):
+        img_c, par_c, bas_c, per = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = img_c.device
+        h, w, kind = cfg["h"], cfg["w"], cfg["kind"]
+        need_img, need_par = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_src = torch.zeros_like(img_c) if need_img else None
+        g_par = None
+        if need_par:
+            g_par = torch.empty_like(par_c) if kind in (PARAM_FLOW, PARAM_COORDS) else torch.zeros_like(par_c)
+        d = _desc(cfg["sampler"], kind, img_c, par_c, h, w, basis=bas_c, start=per, start_x=cfg["sx"],
+                  start_y=cfg["sy"], divide=cfg["divide"], grad_out=_f32(gout), grad_src=g_src, grad_param=g_par)
+        _run_warp([d], dev, backward=True)
+        return g_src, (g_par.view(cfg["pshape"]) if g_par is not None else None), None, None
+
+
+def warp(img, param, kind=PARAM_FLOW, sampler=S1, out_hw=None, start=0, basis=None, divide=1, return_mask=False,
+         return_flow=False, return_indices=False):
+    """Bilinear warp of `img` (B,C,Hs,Ws) at coordinates given by `param` (see dmh_param_kind).
+
+    Returns out (B,C,h,w); with return_mask also the M1 validity mask (B,h,w) bool; with
+    return_flow the generated flow (B,2,h,w); with return_indices the clamped integer corners
+    (4,B,h,w) int32 [x0,y0,x1,y1].  Differentiable w.r.t. img and param."""
+    if img.dim() != 4:
+        raise ValueError("img must be (B,C,H,W)")
+    if kind in (PARAM_FLOW, PARAM_COORDS):
+        h, w = param.shape[-2:]
+    else:
+        h, w = out_hw if out_hw is not None else img.shape[-2:]
+    cfg = dict(sampler=sampler, kind=kind, h=int(h), w=int(w), start=start, divide=int(divide), mask=return_mask,
+               flow=return_flow, indices=return_indices)
+    res = _Warp.apply(img, param, basis, cfg)
+    out, extras = res[0], list(res[1:])
+    ret = [out]
+    if return_mask:
+        ret.append(extras.pop(0).bool())
+    if return_flow:
+        ret.append(extras.pop(0))
+    if return_indices:
+        ret.append(extras.pop(0))
+    return ret[0] if len(ret) == 1 else tuple(ret)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused warp + mask + masked-L1 (+ gradients) (A13, A14)
+# ----------------------------------------------------------------------------------------------
+class WarpTerm:
+    """One loss term: mean-style masked L1 between `target` and warp(`src`, `param`)."""
+
+    def __init__(self, src, target, param, soft_mask=None, sample_weight=None):
+        self.src, self.target, self.param = src, target, param
+        self.soft_mask, self.sample_weight = soft_mask, sample_weight
+
+
+_SLOTS = 5  # tensors per term: src, target, param, soft_mask, sample_weight
+
+
+class _WarpLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, basis, *flat):
+        n = len(flat) // _SLOTS
+        dev = _cuda(basis, *flat)
+        bas_c = _f32(basis)
+        terms = [[_f32(t) for t in flat[i * _SLOTS:(i + 1) * _SLOTS]] for i in range(n)]
+        B, Cc, Hs, Ws = terms[0][0].shape
+        h, w = terms[0][1].shape[-2:]
+        for src, tgt, par, soft, sw in terms:
+            if tuple(tgt.shape) != (B, Cc, h, w) or src.shape[:2] != (B, Cc):
+                raise ValueError("warp_loss: src (B,C,Hs,Ws) / target (B,C,h,w) shapes disagree")
+            _param_shape_check(cfg["kind"], par, B, h, w, cfg["divide"])
+            if soft is not None and soft.numel() != B * h * w:
+                raise ValueError("warp_loss: soft_mask must be (B,1,h,w)")
+            if sw is not None and sw.numel() != B:
+                raise ValueError("warp_loss: sample_weight must be (B,)")
+        sx, sy, per = _start_args(cfg["start"], B, dev)
+        scale = float(cfg["weight"]) / float(B * Cc * h * w)
+
+        needs = ctx.needs_input_grad[2:]
+        any_grad = any(needs)
+        fused = bool(cfg["fused"]) and any_grad
+        # one flat zeroed workspace: [loss accumulators (double) | gradients of every distinct input]
+        acc_floats = 2 * n * B
+        slots = {}     # (term, slot) -> (offset, numel) into the flat gradient region
+        owners = {}    # data_ptr -> (offset, numel)   (img1 is target of one term and source of the other)
+        total = acc_floats
+        if fused:
+            for i, tl in enumerate(terms):
+                for s in (0, 1, 2, 3):
+                    if tl[s] is None or not needs[i * _SLOTS + s]:
+                        continue
+                    key = (tl[s].data_ptr(), tl[s].numel())
+                    if key not in owners:
+                        owners[key] = (total, tl[s].numel())
+                        total += tl[s].numel()
+                    slots[(i, s)] = owners[key]
+        ws = torch.zeros(total, device=dev, dtype=torch.float32)
+        acc = ws[:acc_floats].view(torch.float64)
+
+        def gbuf(i, s):
+            if (i, s) not in slots:
+                return None
+            o, m = slots[(i, s)]
+            return ws[o:o + m]
+
+        descs = []
+        for i, (src, tgt, par, soft, sw) in enumerate(terms):
+            descs.append(_desc(cfg["sampler"], cfg["kind"], src, par, h, w, basis=bas_c, start=per, start_x=sx,
+                               start_y=sy, divide=cfg["divide"], target=tgt, soft_mask=soft, sample_weight=sw,
+                               use_border_mask=cfg["border_mask"], loss_form=cfg["loss_form"], grad_loss_scale=scale,
+                               compute_grads=fused, loss_acc=acc[i * B:(i + 1) * B], grad_src=gbuf(i, 0),
+                               grad_target=gbuf(i, 1), grad_param=gbuf(i, 2), grad_soft_mask=gbuf(i, 3)))
+        _run_warp(descs, dev)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        acc_ptrs = (C.c_void_p * n)(*[acc[i * B:(i + 1) * B].data_ptr() for i in range(n)])
+        sw_ptrs = (C.c_void_p * n)(*[_p(tl[4]) for tl in terms])
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_loss_finish(acc_ptrs, sw_ptrs, n, B, scale, _p(loss), _stream(dev)), "loss_finish")
+
+        ctx.cfg = dict(cfg, sx=sx, sy=sy, scale=scale, n=n, fused=fused, B=B, h=h, w=w, acc_floats=acc_floats)
+        ctx.slots = slots
+        ctx.shapes = [None if t is None else t.shape for t in flat]
+        if fused:
+            ctx.save_for_backward(ws)
+        else:
+            ctx.save_for_backward(bas_c, per, *[t for tl in terms for t in tl])
+            ctx.none_mask = [t is None for tl in terms for t in tl]
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg = ctx.cfg
+        n, B, h, w = cfg["n"], cfg["B"], cfg["h"], cfg["w"]
+        needs = ctx.needs_input_grad[2:]
+        g = _f32(g)
+        dev = g.device
+        if cfg["fused"]:
+            (ws,) = ctx.saved_tensors
+            slots = ctx.slots
+            nf = ws.numel() - cfg["acc_floats"]
+            if nf > 0:
+                with torch.cuda.device(dev):
+                    L.check(L.lib().dmh_scale_inplace(ws[cfg["acc_floats"]:].data_ptr(), nf, _p(g), _stream(dev)),
+                            "scale_inplace")
+        else:
+            saved = list(ctx.saved_tensors)
+            bas_c, per = saved[0], saved[1]
+            flat = saved[2:]
+            terms = [flat[i * _SLOTS:(i + 1) * _SLOTS] for i in range(n)]
+            slots, owners, total = {}, {}, 0
+            for i, tl in enumerate(terms):
+                for s in (0, 1, 2, 3):
+                    if tl[s] is None or not needs[i * _SLOTS + s]:
+                        continue
+                    key = (tl[s].data_ptr(), tl[s].numel())
+                    if key not in owners:
+                        owners[key] = (total, tl[s].numel())
+                        total += tl[s].numel()
+                    slots[(i, s)] = owners[key]
+            ws = torch.zeros(max(total, 1), device=dev, dtype=torch.float32)
+            cfgacc = 0
+
+            def gbuf(i, s):
+                if (i, s) not in slots:
+                    return None
+                o, m = slots[(i, s)]
+                return ws[o:o + m]
+
+            descs = []
+            for i, (src, tgt, par, soft, sw) in enumerate(terms):
+                descs.append(_desc(cfg["sampler"], cfg["kind"], src, par, h, w, basis=bas_c, start=per,
+                                   start_x=cfg["sx"], start_y=cfg["sy"], divide=cfg["divide"], target=tgt,
+                                   soft_mask=soft, sample_weight=sw, use_border_mask=cfg["border_mask"],
+                                   loss_form=cfg["loss_form"], grad_loss_scale=cfg["scale"], grad_loss=g,
+                                   grad_src=gbuf(i, 0), grad_target=gbuf(i, 1), grad_param=gbuf(i, 2),
+                                   grad_soft_mask=gbuf(i, 3)))
+            _run_warp(descs, dev, backward=True)
+            cfg = dict(cfg, acc_floats=cfgacc)
+        # hand every distinct buffer back exactly once (autograd sums duplicates of the same input)
+        grads, seen = [], set()
+        for i in range(n):
+            for s in range(_SLOTS):
+                k = (i, s)
+                if k in slots and slots[k] not in seen:
+                    seen.add(slots[k])
+                    o, m = slots[k]
+                    grads.append(ws[o:o + m].view(ctx.shapes[i * _SLOTS + s]))
+                else:
+                    grads.append(None)
+        return (None, None) + tuple(grads)
+
+
+def warp_loss(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DIFF, border_mask=True, weight=1.0,
+              basis=None, divide=1, start=0, fused=True):
+    """sum over `terms` of  weight * mean_{b,c,y,x}( sample_weight[b] * L(m, target, warp(src, param)) ).
+
+    One kernel launch evaluates every term (e.g. both directions of a pair): flow generation,
+    bilinear sampling, the M1 validity mask, the masked L1 and - when `fused` and an input
+    requires grad - the gradients to src / target / param / soft_mask in the same pass (the
+    backward then only rescales them by the upstream gradient, a no-op when it is 1).
+    With fused=False gradients are produced by the separate backward kernel.
+    L = |m*t - m*w| (LOSS_MASKED_DIFF, HEM/loss/losses.py:142-146) or m*|w - t| (LOSS_DIFF_MASKED,
+    classifier_free_guidance.py:799-806); m = M1 (if border_mask) * soft_mask."""
+    if isinstance(terms, WarpTerm):
+        terms = [terms]
+    flat = []
+    for t in terms:
+        flat += [t.src, t.target, t.param, t.soft_mask, t.sample_weight]
+    cfg = dict(kind=kind, sampler=sampler, loss_form=loss_form, border_mask=bool(border_mask), weight=float(weight),
+               divide=int(divide), start=start, fused=bool(fused))
+    return _WarpLoss.apply(cfg, basis, *flat)
+
+
+# ----------------------------------------------------------------------------------------------
+# masks, plain L1
+# ----------------------------------------------------------------------------------------------
+def border_mask(flow, as_float=False):
+    """get_gt_correspondence_mask / create_border_mask (flow_and_mapping_operations.py:40-71)."""
+    dev = _cuda(flow)
+    f = _f32(flow)
+    B, _, h, w = f.shape
+    if as_float:
+        out = torch.empty(B, h, w, device=dev, dtype=torch.float32)
+        a, b = None, _p(out)
+    else:
+        out = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
+        a, b = _p(out), None
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_border_mask(_p(f), a, b, B, h, w, _stream(dev)), "border_mask")
+    return out if as_float else out.bool()
+
+
+def zero_border_mask(image, eps=1e-6):
+    """define_mask_zero_borders (flow_and_mapping_operations.py:6-37): image (B,3,h,w) -> bool (B,h,w)."""
+    dev = _cuda(image)
+    im = _f32(image)
+    B, c, h, w = im.shape
+    if c != 3:
+        raise ValueError("zero_border_mask expects (B,3,h,w)")
+    out = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_zero_border_mask(_p(im), _p(out), B, h, w, float(eps), _stream(dev)), "zero_border_mask")
+    return out.bool()
+
+
+class _L1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, reduction):
+        dev = _cuda(a, b)
+        ac, bc = _f32(a), _f32(b.expand_as(a) if b.shape != a.shape else b)
+        n = ac.numel()
+        acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_l1_sum(_p(ac), _p(bc), n, _p(acc), _stream(dev)), "l1_sum")
+            scale = 1.0 / n if reduction == "mean" else 1.0
+            loss = torch.empty((), device=dev, dtype=torch.float32)
+            ptrs = (C.c_void_p * 1)(acc.data_ptr())
+            L.check(L.lib().dmh_loss_finish(ptrs, None, 1, 1, scale, _p(loss), _stream(dev)), "loss_finish")
+        ctx.save_for_backward(ac, bc)
+        ctx.scale = scale
+        ctx.shapes = (a.shape, b.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ac, bc = ctx.saved_tensors
+        dev = ac.device
+        ga = torch.empty_like(ac) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(bc) if ctx.needs_input_grad[1] else None
+        if ga is None and gb is None:
+            return None, None, None
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_l1_backward(_p(ac), _p(bc), ac.numel(), _p(_f32(g)), ctx.scale, _p(ga), _p(gb),
+                                            _stream(dev)), "l1_backward")
+        if gb is not None and ctx.shapes[1] != ctx.shapes[0]:
+            gb = gb.sum_to_size(ctx.shapes[1])
+        return ga, gb, None
+
+
+def l1_loss(a, b, reduction="mean"):
+    """nn.L1Loss(reduction)(a, b) as used by LossL1 (HEM/loss/losses.py:10-17)."""
+    if reduction not in ("mean", "sum"):
+        raise ValueError(f"l1_loss: unsupported reduction {reduction!r}")
+    return _L1.apply(a, b, reduction)
+
+
+# ----------------------------------------------------------------------------------------------
+# DGM condition rendering (A16, A17), eval metric (A18), least-squares homography (next row 1)
+# ----------------------------------------------------------------------------------------------
+def flow_to_rgb(flow, max_flow=256.0, in_channels_last=False, out_channels_last=False):
+    """flow_to_image()/visulize_flow() (ddpm.py:1471-1502).  flow (B,2,h,w) [or (B,h,w,2)] -> rgb in [0,1]."""
+    dev = _cuda(flow)
+    f = _f32(flow)
+    if in_channels_last:
+        B, h, w, _ = f.shape
+    else:
+        B, _, h, w = f.shape
+    max_flow = max(float(max_flow), 1.0)
+    out = torch.empty((B, h, w, 3) if out_channels_last else (B, 3, h, w), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_flow_to_rgb(_p(f), _p(out), B, h, w, max_flow, int(in_channels_last),
+                                        int(out_channels_last), _stream(dev)), "flow_to_rgb")
+    return out
+
+
+def warp_perspective(img, H, dsize, channels_last=False):
+    """cv2.warpPerspective(img, H, dsize=(w,h)) with default flags, batched (ddpm.py:1520-1529).
+    img (B,C,Hs,Ws) [or (B,Hs,Ws,C)] fp32; H (B,3,3) (any float dtype; used as float64)."""
+    dev = _cuda(img, H)
+    im = _f32(img)
+    Hc = H.to(torch.float64).contiguous()
+    if channels_last:
+        B, Hs, Ws, Cc = im.shape
+    else:
+        B, Cc, Hs, Ws = im.shape
+    w, h = int(dsize[0]), int(dsize[1])
+    if Hc.numel() != B * 9:
+        raise ValueError("warp_perspective: H must be (B,3,3)")
+    out = torch.empty((B, h, w, Cc) if channels_last else (B, Cc, h, w), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_warp_perspective(_p(im), _p(Hc), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last),
+                                             _stream(dev)), "warp_perspective")
+    return out
+
+
+def eval_point_error(pts, flow_f, flow_b):
+    """compute_eval_results() (HEM/loss/losses.py:263-296): pts (B,P,2,2), flows (B,h,w,2) -> (B,)."""
+    dev = _cuda(pts, flow_f, flow_b)
+    p, ff, fb = _f32(pts), _f32(flow_f), _f32(flow_b)
+    B, P = p.shape[:2]
+    _, h, w, _ = ff.shape
+    err = torch.empty(B, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_eval_point_error(_p(p), _p(ff), _p(fb), _p(err), B, P, h, w, _stream(dev)),
+                "eval_point_error")
+    return err
+
+
+def flow_to_homography_ls(flow):
+    """homo_gen() (ddpm.py:1647-1661): least-squares DLT over all pixels.  (B,2,h,w) -> (B,1,3,3) float64."""
+    dev = _cuda(flow)
+    f = _f32(flow)
+    B, _, h, w = f.shape
+    H = torch.empty(B, 1, 3, 3, device=dev, dtype=torch.float64)
+    ws = torch.empty(B * 45, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_flow_to_homography_ls(_p(f), _p(H), _p(ws), B, h, w, _stream(dev)),
+                "flow_to_homography_ls")
+    return H
