@@ -7,20 +7,28 @@
 // HEM/utils_operations/flow_and_mapping_operations.py:40-71, HEM/loss/losses.py:10-17,142-146,
 // DGM/denoising_diffusion_models/classifier_free_guidance.py:784-806.
 //
-// Layout: one CTA = 64x8 output pixels of one sample (256 threads, a warp owns one output
-// row: lanes are consecutive pixels, so source taps of a warp fall on 1-2 consecutive
-// 128-byte lines per tap row, target / output / mask accesses are fully coalesced and the
-// scatter of the backward lands on consecutive addresses that the LSU folds into
-// per-sector reductions).  Per-sample reductions (loss, dL/dH, dL/dw) go warp shuffle ->
-// shared memory -> one atomic per CTA.
+// Work decomposition (B200: 148 SMs, HBM-bound gather/stencil, no tensor cores):
+//   * one CTA = a 64 x 64 tile of one sample of one term (256 threads = 2 x 4 warps);
+//   * a warp owns 32 consecutive columns, so target / output / mask traffic is one fully
+//     coalesced 128-byte line per row and the four source taps of a warp fall on 1-2 lines;
+//   * a thread walks 16 consecutive rows of ITS column.  Everything that only depends on the
+//     column (h0*x, h3*x, h6*x) is hoisted; per-sample reductions (loss, dL/dH, dL/dw) stay in
+//     registers for 16 pixels and then go warp shuffle -> shared memory -> ONE atomic per CTA
+//     and value;
+//   * backward scatter: the bottom taps of row r and the top taps of row r+1 of a column hit
+//     the same two source addresses under any near-rigid warp, so they are merged in registers
+//     and each column issues ~2 (not 4) fire-and-forget REDG per pixel and channel; lanes are
+//     consecutive addresses, so a warp-wide REDG is one coalesced 128-byte reduction at L2.
 #include "dmh_common.cuh"
 
 namespace dmh {
 
-constexpr int TW = 64;   // tile width  (2 pixels per thread, 32 apart)
-constexpr int TH = 8;    // tile height (one row per warp)
-constexpr int NPX = 2;
 constexpr int NT = 256;
+constexpr int WX = 2;          // warps along x in a CTA
+constexpr int WY = 4;          // warps along y in a CTA
+constexpr int RPT = 16;        // rows per thread
+constexpr int TW = 32 * WX;    // tile width  (64)
+constexpr int TH = WY * RPT;   // tile height (64)
 constexpr int kMaxBatch = 4;
 
 enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
@@ -53,8 +61,8 @@ __device__ __forceinline__ void make_taps(float cx, float cy, int Hs, int Ws, Ta
       cy = fminf(fmaxf(cy, 0.f), my);
     }
     // floor -> int32 -> +1 -> clamp (utils.py:463-471); keep the cast in range
-    const float fxl = fminf(fmaxf(floorf(cx), -1.0e9f), 1.0e9f);
-    const float fyl = fminf(fmaxf(floorf(cy), -1.0e9f), 1.0e9f);
+    const float fxl = fminf(fmaxf(floorf(cx), -2.0f), 1.0e9f);
+    const float fyl = fminf(fmaxf(floorf(cy), -2.0f), 1.0e9f);
     int x0 = (int)fxl, y0 = (int)fyl;
     int x1 = x0 + 1, y1 = y0 + 1;
     x0 = min(max(x0, 0), Ws - 1);
@@ -70,10 +78,11 @@ __device__ __forceinline__ void make_taps(float cx, float cy, int Hs, int Ws, Ta
     t.wb = mul_rn(t.ax1, t.ay0);
     t.wc = mul_rn(t.ax0, t.ay1);
     t.wd = mul_rn(t.ax0, t.ay0);
-    t.ia = y0 * Ws + x0;
-    t.ib = y1 * Ws + x0;
-    t.ic = y0 * Ws + x1;
-    t.id = y1 * Ws + x1;
+    const int r0 = y0 * Ws, r1 = y1 * Ws;
+    t.ia = r0 + x0;
+    t.ib = r1 + x0;
+    t.ic = r0 + x1;
+    t.id = r1 + x1;
     x0o = x0; y0o = y0; x1o = x1; y1o = y1;
   } else {
     // normalise to [-1,1] exactly as the reference does, then ATen's align_corners=True
@@ -126,8 +135,13 @@ __device__ __forceinline__ float blend(const Taps& t, float Ia, float Ib, float 
 }
 
 template <int SAMPLER, int PARAM, int PASS, int CT>
-__global__ void __launch_bounds__(NT) warp_kernel(const __grid_constant__ WarpBatch batch) {
+__global__ void __launch_bounds__(NT, (CT == 1 && PARAM != DMH_PARAM_BASIS8) ? 3 : 2)
+    warp_kernel(const __grid_constant__ WarpBatch batch) {
   const dmh_warp_desc& d = batch.d[blockIdx.y];
+  constexpr bool kGrad = (PASS != PASS_FWD);
+  constexpr bool kOut = (PASS != PASS_BWD);
+  constexpr bool kCombine = kGrad && (CT > 0);  // merge vertically adjacent taps before REDG
+  constexpr int CC = (CT > 0) ? CT : 1;
   const int C = CT ? CT : d.C;
   const int h = d.h, w = d.w, Hs = d.Hs, Ws = d.Ws;
   const int tiles_x = (w + TW - 1) / TW, tiles_y = (h + TH - 1) / TH;
@@ -136,20 +150,22 @@ __global__ void __launch_bounds__(NT) warp_kernel(const __grid_constant__ WarpBa
   t -= b * tiles_x * tiles_y;
   const int tyi = t / tiles_x, txi = t - tyi * tiles_x;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int y = tyi * TH + wrp;
-  const bool row_live = y < h;
-  constexpr bool kGrad = (PASS != PASS_FWD);
-  constexpr bool kOut = (PASS != PASS_BWD);
+  const int x = txi * TW + (wrp % WX) * 32 + lane;
+  const int y_begin = tyi * TH + (wrp / WX) * RPT;
+  const int y_end = min(y_begin + RPT, h);
+  const bool col_live = x < w;
 
-  const size_t plane_o = (size_t)h * w;
-  const size_t plane_s = (size_t)Hs * Ws;
+  const int plane_o = h * w;      // validated < 2^31 on the host
+  const int plane_s = Hs * Ws;
+  const size_t img_o = (size_t)b * C * plane_o;   // first output-shaped plane of sample b
+  const size_t img_s = (size_t)b * C * plane_s;
 
   float sx = d.start_x, sy = d.start_y;
   if (d.start) {
     sx = __ldg(d.start + 2 * b);
     sy = __ldg(d.start + 2 * b + 1);
   }
-  const float gy = add_rn((float)y, sy);
+  const float gx = add_rn((float)x, sx);
 
   // per-sample parameters
   float hm[9];
@@ -162,9 +178,16 @@ __global__ void __launch_bounds__(NT) warp_kernel(const __grid_constant__ WarpBa
 #pragma unroll
     for (int k = 0; k < 8; ++k) bw[k] = __ldg(d.param + (size_t)b * 8 + k);
   }
+  const bool single_h = (PARAM == DMH_PARAM_HOMOGRAPHY) && (d.divide == 1);
+  // WarpImages (S1B) applies H to the un-offset grid and adds `start` afterwards
+  // (HEM/model/utils.py:171-192); get_flow applies it to grid + start (utils.py:400-440).
+  const float hx = (SAMPLER == DMH_S1B) ? (float)x : gx;
 
   const bool want_mask = (d.valid != nullptr) || d.use_border_mask;
   const bool has_loss = (d.loss_form != DMH_LOSS_NONE) && (d.target != nullptr);
+  const bool masked_diff = (d.loss_form == DMH_LOSS_MASKED_DIFF);
+  const bool want_gsrc = kGrad && (d.grad_src != nullptr);
+  const bool want_gpar = kGrad && (d.grad_param != nullptr);
 
   float gscale = 0.f;
   if (kGrad && has_loss) {
@@ -174,211 +197,276 @@ __global__ void __launch_bounds__(NT) warp_kernel(const __grid_constant__ WarpBa
   }
 
   float lsum = 0.f;
+  // HOMOGRAPHY: column-wise partial sums  sa = sum a, say = sum a*hy  (a = gcx/T, b = gcy/T,
+  // c = -(a*qx + b*qy)); the hx factor is constant per thread and applied once at the end.
+  // BASIS8: gacc[k] = sum gcx*bx_k + gcy*by_k.
   float gacc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) gacc[k] = 0.f;
 
+  // vertically merged scatter state (kCombine): bottom taps of the previous row
+  int p_ib = -1, p_id = -1;
+  float pB[CC], pD[CC];
 #pragma unroll
-  for (int i = 0; i < NPX; ++i) {
-    const int x = txi * TW + lane + 32 * i;
-    const bool live = row_live && (x < w);
-    if (!live) continue;
-    const size_t po = (size_t)y * w + x;  // offset in an output plane
-    const float gx = add_rn((float)x, sx);
+  for (int c = 0; c < CC; ++c) pB[c] = pD[c] = 0.f;
 
-    // ---- sampling coordinate ------------------------------------------------------
-    float fx = 0.f, fy = 0.f, cx, cy;
-    float qX = 0.f, qY = 0.f, qT = 1.f;  // homography numerators / denominator (for grads)
-    float hx = gx, hy = gy;              // grid point the homography is applied to
-    int cell = 0;
-    if (PARAM == DMH_PARAM_FLOW) {
-      fx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
-      fy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
-      cx = add_rn(gx, fx);
-      cy = add_rn(gy, fy);
-    } else if (PARAM == DMH_PARAM_COORDS) {
-      cx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
-      cy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
-      fx = sub_rn(cx, gx);
-      fy = sub_rn(cy, gy);
-    } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
-      if (d.divide != 1) {
-        const int dv = d.divide;
-        cell = min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1);
-        const float* Hp = d.param + ((size_t)b * dv * dv + cell) * 9;
+  if (col_live) {
+    for (int y = y_begin; y < y_end; ++y) {
+      const int po = y * w + x;  // offset in an output plane
+      const float gy = add_rn((float)y, sy);
+
+      // ---- sampling coordinate ------------------------------------------------------
+      float fx = 0.f, fy = 0.f, cx, cy;
+      float qx = 0.f, qy = 0.f, qT = 1.f;  // X/T', Y/T', T' (for the homography gradient)
+      float hy = gy;
+      int cell = 0;
+      if (PARAM == DMH_PARAM_FLOW) {
+        fx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
+        fy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
+        cx = add_rn(gx, fx);
+        cy = add_rn(gy, fy);
+      } else if (PARAM == DMH_PARAM_COORDS) {
+        cx = __ldg(d.param + ((size_t)b * 2) * plane_o + po);
+        cy = __ldg(d.param + ((size_t)b * 2 + 1) * plane_o + po);
+        fx = sub_rn(cx, gx);
+        fy = sub_rn(cy, gy);
+      } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+        if (!single_h) {
+          const int dv = d.divide;
+          cell = min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1);
+          const float* Hp = d.param + ((size_t)b * dv * dv + cell) * 9;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) hm[k] = __ldg(Hp + k);
-      }
-      // WarpImages (S1B) applies H to the un-offset grid and adds `start` afterwards
-      // (HEM/model/utils.py:171-192); get_flow applies it to grid + start (utils.py:400-440).
-      hx = (SAMPLER == DMH_S1B) ? (float)x : gx;
-      hy = (SAMPLER == DMH_S1B) ? (float)y : gy;
-      // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
-      qX = add_rn(add_rn(mul_rn(hm[0], hx), mul_rn(hm[1], hy)), hm[2]);
-      qY = add_rn(add_rn(mul_rn(hm[3], hx), mul_rn(hm[4], hy)), hm[5]);
-      qT = add_rn(add_rn(mul_rn(hm[6], hx), mul_rn(hm[7], hy)), hm[8]);
-      if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
-      fx = sub_rn(div_rn(qX, qT), hx);
-      fy = sub_rn(div_rn(qY, qT), hy);
-      cx = add_rn(gx, fx);
-      cy = add_rn(gy, fy);
-    } else {  // BASIS8: acc = b0*w0; acc += bk*wk, products rounded separately (A12)
-      const float* bp = d.basis + po;
-      fx = mul_rn(__ldg(bp), bw[0]);
-      fy = mul_rn(__ldg(bp + plane_o), bw[0]);
-#pragma unroll
-      for (int k = 1; k < 8; ++k) {
-        fx = add_rn(fx, mul_rn(__ldg(bp + (size_t)(2 * k) * plane_o), bw[k]));
-        fy = add_rn(fy, mul_rn(__ldg(bp + (size_t)(2 * k + 1) * plane_o), bw[k]));
-      }
-      cx = add_rn(gx, fx);
-      cy = add_rn(gy, fy);
-    }
-
-    // ---- M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h ----------
-    float m = 1.f;
-    bool m1 = true;
-    if (want_mask) {
-      const float mx = (PARAM == DMH_PARAM_COORDS) ? cx : add_rn(fx, (float)x);
-      const float my = (PARAM == DMH_PARAM_COORDS) ? cy : add_rn(fy, (float)y);
-      m1 = (mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h);
-      if (kOut && d.valid) d.valid[(size_t)b * plane_o + po] = m1 ? 1 : 0;
-      if (d.use_border_mask) m = m1 ? 1.f : 0.f;
-    }
-    float soft = 1.f;
-    if (d.soft_mask) {
-      soft = __ldg(d.soft_mask + (size_t)b * plane_o + po);
-      m = mul_rn(m, soft);
-    }
-    if (kOut && d.flow_out) {
-      d.flow_out[((size_t)b * 2) * plane_o + po] = fx;
-      d.flow_out[((size_t)b * 2 + 1) * plane_o + po] = fy;
-    }
-
-    // ---- taps ------------------------------------------------------------------------------
-    Taps tp;
-    int x0, y0, x1, y1;
-    make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
-    if (kOut && d.indices) {
-      const size_t n = (size_t)d.B * plane_o, o = (size_t)b * plane_o + po;
-      d.indices[o] = x0;
-      d.indices[n + o] = y0;
-      d.indices[2 * n + o] = x1;
-      d.indices[3 * n + o] = y1;
-    }
-
-    float gcx = 0.f, gcy = 0.f, gmask = 0.f;
-#pragma unroll(CT ? CT : 1)
-    for (int c = 0; c < C; ++c) {
-      const float* sp = d.src + ((size_t)b * C + c) * plane_s;
-      const size_t oo = ((size_t)b * C + c) * plane_o + po;
-      float Ia = __ldg(sp + tp.ia), Ib = __ldg(sp + tp.ib), Ic = __ldg(sp + tp.ic), Id = __ldg(sp + tp.id);
-      if (SAMPLER == DMH_S2_ZEROS) {
-        Ia = tp.va ? Ia : 0.f; Ib = tp.vb ? Ib : 0.f; Ic = tp.vc ? Ic : 0.f; Id = tp.vd ? Id : 0.f;
-      }
-      const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
-      if (kOut && d.out) d.out[oo] = wv;
-      float go = 0.f;  // dL/d(out)
-      if (kGrad && PASS == PASS_BWD && d.grad_out) go = __ldg(d.grad_out + oo);
-      if (has_loss) {
-        const float tv = __ldg(d.target + oo);
-        float s, gm_c;
-        if (d.loss_form == DMH_LOSS_MASKED_DIFF) {
-          const float u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));
-          if (kOut) lsum += fabsf(u);
-          s = sign_of(u);                 // d|u|/d(tv) = m*s ; d/d(wv) = -m*s ; d/dm = s*(tv-wv)
-          gm_c = s * (tv - wv);
-          s = m * s;
+          for (int k = 0; k < 9; ++k) hm[k] = __ldg(Hp + k);
+        }
+        hy = (SAMPLER == DMH_S1B) ? (float)y : gy;
+        float qX, qY;
+        if (SAMPLER == DMH_S1B) {
+          // torch.bmm(H, goal) on the CPU (MKL sgemm, k = 3): acc = h0*x; acc = fma(h1, y, acc);
+          // acc = acc + h2   (pinned against the reference in tests/test_oracle_vs_reference.py)
+          qX = add_rn(__fmaf_rn(hm[1], hy, mul_rn(hm[0], hx)), hm[2]);
+          qY = add_rn(__fmaf_rn(hm[4], hy, mul_rn(hm[3], hx)), hm[5]);
+          qT = add_rn(__fmaf_rn(hm[7], hy, mul_rn(hm[6], hx)), hm[8]);
         } else {
-          const float u = sub_rn(wv, tv);
-          if (kOut) lsum += m * fabsf(u);
-          gm_c = fabsf(u);
-          s = -m * sign_of(u);            // d/d(tv) = -m*sign ; d/d(wv) = +m*sign
+          // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
+          qX = add_rn(add_rn(mul_rn(hm[0], hx), mul_rn(hm[1], hy)), hm[2]);
+          qY = add_rn(add_rn(mul_rn(hm[3], hx), mul_rn(hm[4], hy)), hm[5]);
+          qT = add_rn(add_rn(mul_rn(hm[6], hx), mul_rn(hm[7], hy)), hm[8]);
+        }
+        if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
+        qx = div_rn(qX, qT);
+        qy = div_rn(qY, qT);
+        fx = sub_rn(qx, hx);
+        fy = sub_rn(qy, hy);
+        cx = add_rn(gx, fx);
+        cy = add_rn(gy, fy);
+      } else {  // BASIS8: acc = b0*w0; acc += bk*wk, products rounded separately (A12)
+        const float* bp = d.basis + po;
+        fx = mul_rn(__ldg(bp), bw[0]);
+        fy = mul_rn(__ldg(bp + plane_o), bw[0]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+          fx = add_rn(fx, mul_rn(__ldg(bp + (size_t)(2 * k) * plane_o), bw[k]));
+          fy = add_rn(fy, mul_rn(__ldg(bp + (size_t)(2 * k + 1) * plane_o), bw[k]));
+        }
+        cx = add_rn(gx, fx);
+        cy = add_rn(gy, fy);
+      }
+
+      // ---- M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h ----------
+      float m = 1.f;
+      bool m1 = true;
+      if (want_mask) {
+        const float mx = (PARAM == DMH_PARAM_COORDS) ? cx : add_rn(fx, (float)x);
+        const float my = (PARAM == DMH_PARAM_COORDS) ? cy : add_rn(fy, (float)y);
+        m1 = (mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h);
+        if (kOut && d.valid) d.valid[(size_t)b * plane_o + po] = m1 ? 1 : 0;
+        if (d.use_border_mask) m = m1 ? 1.f : 0.f;
+      }
+      if (d.soft_mask) m = mul_rn(m, __ldg(d.soft_mask + (size_t)b * plane_o + po));
+      if (kOut && d.flow_out) {
+        d.flow_out[((size_t)b * 2) * plane_o + po] = fx;
+        d.flow_out[((size_t)b * 2 + 1) * plane_o + po] = fy;
+      }
+
+      // ---- taps ------------------------------------------------------------------------------
+      Taps tp;
+      int x0, y0, x1, y1;
+      make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
+      if (kOut && d.indices) {
+        const size_t n = (size_t)d.B * plane_o, o = (size_t)b * plane_o + po;
+        d.indices[o] = x0;
+        d.indices[n + o] = y0;
+        d.indices[2 * n + o] = x1;
+        d.indices[3 * n + o] = y1;
+      }
+
+      float gcx = 0.f, gcy = 0.f, gmask = 0.f;
+      float cA[CC], cB[CC], cC[CC], cD[CC];
+      bool any_go = false;
+#pragma unroll(CT ? CT : 1)
+      for (int c = 0; c < C; ++c) {
+        const float* sp = d.src + img_s + (size_t)c * plane_s;
+        const size_t oo = img_o + (size_t)c * plane_o + po;
+        float Ia = __ldg(sp + tp.ia), Ib = __ldg(sp + tp.ib), Ic = __ldg(sp + tp.ic), Id = __ldg(sp + tp.id);
+        if (SAMPLER == DMH_S2_ZEROS) {
+          Ia = tp.va ? Ia : 0.f; Ib = tp.vb ? Ib : 0.f; Ic = tp.vc ? Ic : 0.f; Id = tp.vd ? Id : 0.f;
+        }
+        const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
+        if (kOut && d.out) d.out[oo] = wv;
+        float go = 0.f;  // dL/d(out)
+        if (PASS == PASS_BWD && d.grad_out) go = __ldg(d.grad_out + oo);
+        if (has_loss) {
+          const float tv = __ldg(d.target + oo);
+          float s, gm_c;
+          if (masked_diff) {
+            const float u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));
+            if (kOut) lsum += fabsf(u);
+            s = sign_of(u);                 // d|u|/d(tv) = m*s ; d/d(wv) = -m*s ; d/dm = s*(tv-wv)
+            gm_c = s * (tv - wv);
+            s = m * s;
+          } else {
+            const float u = sub_rn(wv, tv);
+            if (kOut) lsum += m * fabsf(u);
+            gm_c = fabsf(u);
+            s = -m * sign_of(u);            // d/d(tv) = -m*sign ; d/d(wv) = +m*sign
+          }
+          if (kGrad) {
+            const float gt = gscale * s;
+            go -= gt;
+            if (d.grad_target && gt != 0.f) red_add(d.grad_target + oo, gt);
+            gmask += gscale * gm_c;
+          }
         }
         if (kGrad) {
-          const float gt = gscale * s;
-          go -= gt;
-          if (d.grad_target && gt != 0.f) red_add(d.grad_target + oo, gt);
-          gmask += gscale * gm_c;
+          if (want_gsrc) {
+            const float a_ = (SAMPLER != DMH_S2_ZEROS || tp.va) ? tp.wa * go : 0.f;
+            const float b_ = (SAMPLER != DMH_S2_ZEROS || tp.vb) ? tp.wb * go : 0.f;
+            const float c_ = (SAMPLER != DMH_S2_ZEROS || tp.vc) ? tp.wc * go : 0.f;
+            const float d_ = (SAMPLER != DMH_S2_ZEROS || tp.vd) ? tp.wd * go : 0.f;
+            if (kCombine) {
+              cA[c] = a_; cB[c] = b_; cC[c] = c_; cD[c] = d_;
+              any_go = any_go || (go != 0.f);
+            } else if (go != 0.f) {
+              float* gp = d.grad_src + img_s + (size_t)c * plane_s;
+              red_add(gp + tp.ia, a_);
+              red_add(gp + tp.ib, b_);
+              red_add(gp + tp.ic, c_);
+              red_add(gp + tp.id, d_);
+            }
+          }
+          // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
+          gcx += go * (tp.ay1 * (Ic - Ia) + tp.ay0 * (Id - Ib));
+          gcy += go * (tp.ax1 * (Ib - Ia) + tp.ax0 * (Id - Ic));
         }
       }
-      if (kGrad) {
-        if (d.grad_src && go != 0.f) {
-          float* gp = d.grad_src + ((size_t)b * C + c) * plane_s;
-          if (SAMPLER != DMH_S2_ZEROS || tp.va) red_add(gp + tp.ia, tp.wa * go);
-          if (SAMPLER != DMH_S2_ZEROS || tp.vb) red_add(gp + tp.ib, tp.wb * go);
-          if (SAMPLER != DMH_S2_ZEROS || tp.vc) red_add(gp + tp.ic, tp.wc * go);
-          if (SAMPLER != DMH_S2_ZEROS || tp.vd) red_add(gp + tp.id, tp.wd * go);
+
+      if (kCombine && want_gsrc && any_go) {
+        float* gp = d.grad_src + img_s;
+        if (p_ib >= 0) {
+          if (p_ib == tp.ia && p_id == tp.ic) {  // previous bottom taps == this row's top taps
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+              cA[c] += pB[c];
+              cC[c] += pD[c];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+              red_add(gp + (size_t)c * plane_s + p_ib, pB[c]);
+              red_add(gp + (size_t)c * plane_s + p_id, pD[c]);
+            }
+          }
         }
-        // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
-        gcx += go * (tp.ay1 * (Ic - Ia) + tp.ay0 * (Id - Ib));
-        gcy += go * (tp.ax1 * (Ib - Ia) + tp.ax0 * (Id - Ic));
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          red_add(gp + (size_t)c * plane_s + tp.ia, cA[c]);
+          red_add(gp + (size_t)c * plane_s + tp.ic, cC[c]);
+          pB[c] = cB[c];
+          pD[c] = cD[c];
+        }
+        p_ib = tp.ib;
+        p_id = tp.id;
+      }
+
+      if (kGrad) {
+        gcx *= tp.gate_x;
+        gcy *= tp.gate_y;
+        if (d.grad_soft_mask)
+          d.grad_soft_mask[(size_t)b * plane_o + po] = (d.use_border_mask && !m1) ? 0.f : gmask;
+        if (want_gpar) {
+          if (PARAM == DMH_PARAM_FLOW || PARAM == DMH_PARAM_COORDS) {
+            d.grad_param[((size_t)b * 2) * plane_o + po] = gcx;
+            d.grad_param[((size_t)b * 2 + 1) * plane_o + po] = gcy;
+          } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+            // flow = q/T' - g  =>  dL/dX = gcx/T', dL/dY = gcy/T', dL/dT = -(gcx*X + gcy*Y)/T'^2
+            const float rT = __frcp_rn(qT);
+            const float ga = gcx * rT, gb = gcy * rT;
+            const float gc = -(ga * qx + gb * qy);
+            if (single_h) {
+              gacc[0] += ga; gacc[1] = fmaf(ga, hy, gacc[1]);
+              gacc[2] += gb; gacc[3] = fmaf(gb, hy, gacc[3]);
+              gacc[4] += gc; gacc[5] = fmaf(gc, hy, gacc[5]);
+            } else {  // mesh of homographies: rare path, straight to global
+              float* gp = d.grad_param + ((size_t)b * d.divide * d.divide + cell) * 9;
+              red_add(gp + 0, ga * hx); red_add(gp + 1, ga * hy); red_add(gp + 2, ga);
+              red_add(gp + 3, gb * hx); red_add(gp + 4, gb * hy); red_add(gp + 5, gb);
+              red_add(gp + 6, gc * hx); red_add(gp + 7, gc * hy); red_add(gp + 8, gc);
+            }
+          } else {
+            const float* bp = d.basis + po;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              gacc[k] += gcx * __ldg(bp + (size_t)(2 * k) * plane_o) + gcy * __ldg(bp + (size_t)(2 * k + 1) * plane_o);
+          }
+        }
       }
     }
-
-    if (kGrad) {
-      gcx *= tp.gate_x;
-      gcy *= tp.gate_y;
-      if (d.grad_soft_mask) d.grad_soft_mask[(size_t)b * plane_o + po] = (d.use_border_mask && !m1) ? 0.f : gmask;
-      if (d.grad_param) {
-        if (PARAM == DMH_PARAM_FLOW || PARAM == DMH_PARAM_COORDS) {
-          d.grad_param[((size_t)b * 2) * plane_o + po] = gcx;
-          d.grad_param[((size_t)b * 2 + 1) * plane_o + po] = gcy;
-        } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
-          // flow = q/T' - g  =>  dX = g/T', dT = -(gcx*X + gcy*Y)/T'^2
-          const float rT = 1.f / qT;
-          const float gX = gcx * rT, gY = gcy * rT;
-          const float gT = -(gcx * qX + gcy * qY) * rT * rT;
-          if (d.divide == 1) {
-            gacc[0] += gX * hx; gacc[1] += gX * hy; gacc[2] += gX;
-            gacc[3] += gY * hx; gacc[4] += gY * hy; gacc[5] += gY;
-            gacc[6] += gT * hx; gacc[7] += gT * hy; gacc[8] += gT;
-          } else {  // mesh of homographies: rare path, straight to global
-            float* gp = d.grad_param + ((size_t)b * d.divide * d.divide + cell) * 9;
-            red_add(gp + 0, gX * hx); red_add(gp + 1, gX * hy); red_add(gp + 2, gX);
-            red_add(gp + 3, gY * hx); red_add(gp + 4, gY * hy); red_add(gp + 5, gY);
-            red_add(gp + 6, gT * hx); red_add(gp + 7, gT * hy); red_add(gp + 8, gT);
-          }
-        } else {
-          const float* bp = d.basis + po;
+    if (kCombine && p_ib >= 0) {
+      float* gp = d.grad_src + img_s;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            gacc[k] += gcx * __ldg(bp + (size_t)(2 * k) * plane_o) + gcy * __ldg(bp + (size_t)(2 * k + 1) * plane_o);
-        }
+      for (int c = 0; c < CC; ++c) {
+        red_add(gp + (size_t)c * plane_s + p_ib, pB[c]);
+        red_add(gp + (size_t)c * plane_s + p_id, pD[c]);
       }
     }
   }
 
   // ---- per-CTA reductions: warp shuffle -> shared -> one atomic per value ---------------------
-  __shared__ float red[NT / 32][10];
-  const bool reduce_param = kGrad && d.grad_param &&
-                            ((PARAM == DMH_PARAM_HOMOGRAPHY && d.divide == 1) || PARAM == DMH_PARAM_BASIS8);
+  const bool reduce_param = want_gpar && (single_h || PARAM == DMH_PARAM_BASIS8);
   const bool reduce_loss = kOut && has_loss && d.loss_acc;
   if (!reduce_param && !reduce_loss) return;
-  if (reduce_loss) {
-    const float v = warp_sum(lsum);
-    if (lane == 0) red[wrp][9] = v;
-  }
-  if (reduce_param) {
+  __shared__ float red[NT / 32][10];
+  float v[10];
+  if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+    // (sum a, sum a*hy) -> (hx*sum a, sum a*hy, sum a) for the three rows of H
+    v[0] = gacc[0] * hx; v[1] = gacc[1]; v[2] = gacc[0];
+    v[3] = gacc[2] * hx; v[4] = gacc[3]; v[5] = gacc[2];
+    v[6] = gacc[4] * hx; v[7] = gacc[5]; v[8] = gacc[4];
+  } else {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float v = warp_sum(gacc[k]);
-      if (lane == 0) red[wrp][k] = v;
+    for (int k = 0; k < 9; ++k) v[k] = gacc[k];
+  }
+  v[9] = lsum;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if ((k == 9) ? reduce_loss : reduce_param) {
+      const float s = warp_sum(v[k]);
+      if (lane == 0) red[wrp][k] = s;
     }
   }
   __syncthreads();
   if (threadIdx.x < 10) {
     const int k = threadIdx.x;
     if ((k == 9 && reduce_loss) || (k < 9 && reduce_param)) {
-      float v = 0.f;
+      float s = 0.f;
 #pragma unroll
-      for (int q = 0; q < NT / 32; ++q) v += red[q][k];
+      for (int q = 0; q < NT / 32; ++q) s += red[q][k];
       if (k == 9) {
-        atomicAdd(d.loss_acc + b, (double)v);
+        atomicAdd(d.loss_acc + b, (double)s);
       } else if (PARAM == DMH_PARAM_HOMOGRAPHY) {
-        red_add(d.grad_param + (size_t)b * 9 + k, v);
+        red_add(d.grad_param + (size_t)b * 9 + k, s);
       } else if (k < 8) {
-        red_add(d.grad_param + (size_t)b * 8 + k, v);
+        red_add(d.grad_param + (size_t)b * 8 + k, s);
       }
     }
   }

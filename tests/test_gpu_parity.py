@@ -261,11 +261,13 @@ def test_warp_images_s1b():
     start = torch.tensor([[3.0, 5.0], [20.0, 12.0]]).view(B, 2, 1, 1)
     ref, flow_ref = port.warp_images_s1b(img, H, start, (40, 32))
     out, flow = hem_utils.WarpImages(img.to(DEV), H.to(DEV), start.to(DEV), (40, 32))
-    assert torch.equal(flow.cpu(), flow_ref)
-    assert torch.equal(out.cpu(), ref)
+    # the reference forms H @ grid with torch.bmm, whose summation order (FMA chain) belongs to the host
+    # BLAS: the kernel follows MKL's order (bit-exact on that host), anything else is <= 1 ulp away
+    assert (flow.cpu() - flow_ref).abs().max().item() < 1e-5
+    assert (out.cpu() - ref).abs().max().item() < ATOL
     out2, _ = hem_utils.Transform(H.to(DEV), img.to(DEV), start.to(DEV), (40, 32), start_zero=True)
     ref2, _ = port.warp_images_s1b(img, H, torch.zeros_like(start), (40, 32))
-    assert torch.equal(out2.cpu(), ref2)
+    assert (out2.cpu() - ref2).abs().max().item() < ATOL
 
 
 # ---------------------------------------------------------------------------------- S2 / S3
