@@ -1,0 +1,403 @@
+// Lean specialisations of the fused warp kernel for the combinations the reference's training and
+// evaluation loops actually run (everything else goes through the general kernel in dmh_warp.cu):
+//
+//   sampler  S1 (get_warp_flow / transformer, HEM/model/utils.py:443-553) or
+//            S3 (flow_warp, ddpm.py:1262-1280 / data_loader.py:84-94)
+//   param    one homography per sample (get_flow, utils.py:400-440) or an explicit flow
+//   pass     forward | backward | forward + gradients in one pass
+//   loss     none | |m*t - m*w| (losses.py:142-146) | m*|w - t| (classifier_free_guidance.py:799-806)
+//   C        1 or 3
+//
+// Same decomposition as the general kernel (64x64 tile per CTA, a warp = 32 consecutive columns, a
+// thread = 16 consecutive rows of one column, vertical tap merging before REDG), but every optional
+// feature is a template parameter, the per-term descriptor is copied to registers once per CTA
+// (no constant-bank indexing in the row loop), all global addresses are one 64-bit base plus a
+// 32-bit element offset, and the row loop is unrolled by two so that the taps / target of row r+1
+// are in flight while row r is blended, reduced and scattered.
+#include "dmh_common.cuh"
+#include "dmh_sampler.cuh"
+#include "dmh_warp_fast.h"
+
+namespace dmh {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int WX = 2, WY = 4, RPT = 16;
+constexpr int TW = 32 * WX, TH = WY * RPT;
+
+enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
+
+// Explicit global-space accesses (the pinned bases below are opaque to the compiler, which would
+// otherwise fall back to generic-address atomics): ld.global.nc, st.global, red.global.add.
+__device__ __forceinline__ float ldg_f(const float* base, unsigned off) {
+  float v;
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(base + off));  // not volatile: free to hoist
+  return v;
+}
+__device__ __forceinline__ void stg_f(float* base, unsigned off, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(base + off), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_u8(uint8_t* base, unsigned off, int v) {
+  asm volatile("st.global.u8 [%0], %1;" ::"l"(base + off), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_f(float* base, unsigned off, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + off), "f"(v) : "memory");
+}
+
+// Pin a per-CTA base pointer into a register pair: every later access is then ONE
+// IMAD.WIDE.U32 (base + 4 * offset) instead of a re-derived 64-bit sum of uniform parts.
+template <typename T>
+__device__ __forceinline__ T* pin(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// PROFILE 0: optional pointers are tested at run time.
+// PROFILE 1 ("dense"): the caller guarantees the layout of the headline paths, so the tests fold away:
+//   forward            out + valid written, no soft mask
+//   backward / fused   border mask on, no soft mask, gradients to src, target and param all wanted,
+//                      loss accumulated (fused); no grad_soft_mask, no grad_out.
+template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS, int PROFILE>
+__global__ void __launch_bounds__(NT, 2) warp_fast_kernel(const __grid_constant__ FastArgs a) {
+  constexpr bool kGrad = (PASS != PASS_FWD);
+  constexpr bool kOut = (PASS != PASS_BWD);
+  constexpr bool kLoss = (LOSS != DMH_LOSS_NONE);
+  constexpr bool kDense = (PROFILE == 1);
+  // ---- per-CTA setup: the term's fields live in registers from here on ----------------------
+  const FastTerm tm = (blockIdx.y == 0) ? a.t[0] : a.t[1];
+  const int h = a.h, w = a.w, Hs = a.Hs, Ws = a.Ws;
+  int t = blockIdx.x;
+  const int per = a.tiles_x * a.tiles_y;
+  const int b = t / per;
+  t -= b * per;
+  const int tyi = t / a.tiles_x, txi = t - tyi * a.tiles_x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int x = txi * TW + (wrp % WX) * 32 + lane;
+  const int y_begin = tyi * TH + (wrp / WX) * RPT;
+  const int y_end = min(y_begin + RPT, h);
+  const bool col_live = x < w;
+  const unsigned plane_o = (unsigned)(h * w), plane_s = (unsigned)(Hs * Ws);
+
+  // sample-b bases; every access below is base[32-bit offset]
+  const float* __restrict__ src = pin(tm.src + (size_t)b * CT * plane_s);
+  const float* __restrict__ tgt = kLoss ? pin(tm.target + (size_t)b * CT * plane_o) : nullptr;
+  const float* __restrict__ gout = (!kDense && PASS == PASS_BWD && tm.grad_out) ? tm.grad_out + (size_t)b * CT * plane_o : nullptr;
+  const float* __restrict__ soft = (!kDense && tm.soft_mask) ? tm.soft_mask + (size_t)b * plane_o : nullptr;
+  const float* __restrict__ flow = (PARAM == DMH_PARAM_FLOW) ? tm.param + (size_t)b * 2 * plane_o : nullptr;
+  const bool has_out = kOut && (kDense ? (PASS == PASS_FWD) : (tm.out != nullptr));
+  const bool has_valid = kOut && (kDense ? (PASS == PASS_FWD) : (tm.valid != nullptr));
+  const bool has_gsrc = kGrad && (kDense || tm.grad_src != nullptr);
+  const bool has_gtgt = kGrad && kLoss && (kDense || tm.grad_target != nullptr);
+  const bool has_gsoft = kGrad && !kDense && (tm.grad_soft_mask != nullptr);
+  const bool has_gflow = kGrad && (PARAM == DMH_PARAM_FLOW) && (kDense || tm.grad_param != nullptr);
+  float* __restrict__ out = has_out ? pin(tm.out + (size_t)b * CT * plane_o) : nullptr;
+  uint8_t* __restrict__ valid = has_valid ? tm.valid + (size_t)b * plane_o : nullptr;
+  float* __restrict__ gsrc = has_gsrc ? pin(tm.grad_src + (size_t)b * CT * plane_s) : nullptr;
+  float* __restrict__ gtgt = has_gtgt ? pin(tm.grad_target + (size_t)b * CT * plane_o) : nullptr;
+  float* __restrict__ gsoft = has_gsoft ? tm.grad_soft_mask + (size_t)b * plane_o : nullptr;
+  float* __restrict__ gflow = has_gflow ? tm.grad_param + (size_t)b * 2 * plane_o : nullptr;
+  const bool want_gH = kGrad && (PARAM == DMH_PARAM_HOMOGRAPHY) && (kDense || tm.grad_param != nullptr);
+  const bool use_border = kDense ? kGrad : (tm.use_border_mask != 0);
+  const bool want_mask = use_border || has_valid;
+
+  const float sx = a.sx, sy = a.sy;
+  const float xf = (float)x;
+  const float gx = add_rn(xf, sx);
+  const float wf = (float)w, hf = (float)h;
+
+  float hm[9];
+  float h0x = 0.f, h3x = 0.f, h6x = 0.f;
+  if (PARAM == DMH_PARAM_HOMOGRAPHY) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hm[k] = __ldg(tm.param + (size_t)b * 9 + k);
+    h0x = mul_rn(hm[0], gx);
+    h3x = mul_rn(hm[3], gx);
+    h6x = mul_rn(hm[6], gx);
+  }
+
+  float gscale = 0.f;
+  if (kGrad && kLoss) {
+    gscale = tm.grad_loss_scale;
+    if (PASS == PASS_BWD && tm.grad_loss) gscale *= __ldg(tm.grad_loss);
+    if (tm.sample_weight) gscale *= __ldg(tm.sample_weight + b);
+  }
+
+  float lsum = 0.f;
+  float sa = 0.f, say = 0.f, sb = 0.f, sby = 0.f, sc = 0.f, scy = 0.f;  // dL/dH column sums
+  int p_ib = -1, p_id = -1;                                              // merged scatter state
+  float pB[CT], pD[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) pB[c] = pD[c] = 0.f;
+
+  if (col_live) {
+    unsigned po = (unsigned)(y_begin * w + x);
+    float yf = (float)y_begin;
+#pragma unroll 2
+    for (int y = y_begin; y < y_end; ++y, po += (unsigned)w, yf += 1.0f) {
+      const float gy = add_rn(yf, sy);
+      // ---- sampling coordinate ------------------------------------------------------------
+      float fx, fy, qx = 0.f, qy = 0.f, qT = 1.f;
+      if (PARAM == DMH_PARAM_FLOW) {
+        fx = ldg_f(flow, po);
+        fy = ldg_f(flow, po + plane_o);
+      } else {
+        // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
+        const float qX = add_rn(add_rn(h0x, mul_rn(hm[1], gy)), hm[2]);
+        const float qY = add_rn(add_rn(h3x, mul_rn(hm[4], gy)), hm[5]);
+        qT = add_rn(add_rn(h6x, mul_rn(hm[7], gy)), hm[8]);
+        if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
+        qx = div_rn(qX, qT);
+        qy = div_rn(qY, qT);
+        fx = sub_rn(qx, gx);
+        fy = sub_rn(qy, gy);
+      }
+      const float cx = add_rn(gx, fx), cy = add_rn(gy, fy);
+
+      // ---- M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h ------------
+      float m = 1.f;
+      bool m1 = true;
+      if (want_mask) {
+        const float mx = add_rn(fx, xf), my = add_rn(fy, yf);
+        m1 = (mx >= 0.f) && (mx <= wf) && (my >= 0.f) && (my <= hf);
+        if (has_valid) stg_u8(valid, po, m1 ? 1 : 0);
+        if (use_border) m = m1 ? 1.f : 0.f;
+      }
+      if (!kDense && soft) m = mul_rn(m, ldg_f(soft, po));
+
+      // ---- taps ---------------------------------------------------------------------------
+      Taps tp;
+      int x0, y0, x1, y1;
+      make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
+
+      float gcx = 0.f, gcy = 0.f, gmask = 0.f;
+      float cA[CT], cB[CT], cC[CT], cD[CT];
+      bool any_go = false;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const unsigned cs = (unsigned)c * plane_s, oo = po + (unsigned)c * plane_o;
+        const float Ia = ldg_f(src, cs + tp.ia), Ib = ldg_f(src, cs + tp.ib);
+        const float Ic = ldg_f(src, cs + tp.ic), Id = ldg_f(src, cs + tp.id);
+        const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
+        if (has_out) stg_f(out, oo, wv);
+        float go = 0.f;  // dL/d(out)
+        if (!kDense && PASS == PASS_BWD && gout) go = ldg_f(gout, oo);
+        if (kLoss) {
+          const float tv = ldg_f(tgt, oo);
+          float u, gm;
+          if (LOSS == DMH_LOSS_MASKED_DIFF) {
+            u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));   // |m*t - m*w|
+            if (kOut) lsum += fabsf(u);
+            gm = gscale * m;                            // d/dt = +gm*sign(u), d/dw = -gm*sign(u)
+          } else {
+            u = sub_rn(tv, wv);                         // m*|w - t|  (same sign convention: u = t - w)
+            if (kOut) lsum += m * fabsf(u);
+            gm = gscale * m;
+          }
+          if (kGrad) {
+            // gt = gm * sign(u): flip gm's sign bit with u's, zero where u == 0
+            float gt = __int_as_float(__float_as_int(gm) ^ (__float_as_int(u) & 0x80000000));
+            gt = (u == 0.f) ? 0.f : gt;
+            go -= gt;
+            if (has_gtgt && gt != 0.f) red_f(gtgt, oo, gt);
+            if (has_gsoft) {
+              const float sg = __int_as_float(__float_as_int(gscale) ^ (__float_as_int(u) & 0x80000000));
+              gmask += (u == 0.f) ? 0.f : ((LOSS == DMH_LOSS_MASKED_DIFF) ? sg * (tv - wv) : gscale * fabsf(u));
+            }
+          }
+        }
+        if (kGrad) {
+          cA[c] = tp.wa * go; cB[c] = tp.wb * go; cC[c] = tp.wc * go; cD[c] = tp.wd * go;
+          any_go = any_go || (go != 0.f);
+          // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
+          gcx = fmaf(go, fmaf(tp.ay1, Ic - Ia, tp.ay0 * (Id - Ib)), gcx);
+          gcy = fmaf(go, fmaf(tp.ax1, Ib - Ia, tp.ax0 * (Id - Ic)), gcy);
+        }
+      }
+
+      if (kGrad && has_gsrc && any_go) {
+        if (p_ib >= 0) {
+          if (p_ib == tp.ia && p_id == tp.ic) {  // previous bottom taps == this row's top taps
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+              cA[c] += pB[c];
+              cC[c] += pD[c];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+              red_f(gsrc, (unsigned)c * plane_s + p_ib, pB[c]);
+              red_f(gsrc, (unsigned)c * plane_s + p_id, pD[c]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          red_f(gsrc, (unsigned)c * plane_s + tp.ia, cA[c]);
+          red_f(gsrc, (unsigned)c * plane_s + tp.ic, cC[c]);
+          pB[c] = cB[c];
+          pD[c] = cD[c];
+        }
+        p_ib = tp.ib;
+        p_id = tp.id;
+      }
+
+      if (kGrad) {
+        gcx *= tp.gate_x;
+        gcy *= tp.gate_y;
+        if (has_gsoft) stg_f(gsoft, po, (use_border && !m1) ? 0.f : gmask);
+        if (has_gflow) {
+          stg_f(gflow, po, gcx);
+          stg_f(gflow, po + plane_o, gcy);
+        }
+        if (want_gH) {
+          // flow = q/T' - g  =>  dL/dX = gcx/T', dL/dY = gcy/T', dL/dT = -(gcx*X + gcy*Y)/T'^2
+          const float rT = rcp_fast(qT);
+          const float ga = gcx * rT, gb = gcy * rT;
+          const float gc = -fmaf(ga, qx, gb * qy);
+          sa += ga; say = fmaf(ga, gy, say);
+          sb += gb; sby = fmaf(gb, gy, sby);
+          sc += gc; scy = fmaf(gc, gy, scy);
+        }
+      }
+    }
+    if (kGrad && has_gsrc && p_ib >= 0) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        red_f(gsrc, (unsigned)c * plane_s + p_ib, pB[c]);
+        red_f(gsrc, (unsigned)c * plane_s + p_id, pD[c]);
+      }
+    }
+  }
+
+  // ---- per-CTA reductions: warp shuffle -> shared -> one atomic per value ---------------------
+  const bool reduce_loss = kOut && kLoss && (kDense || tm.loss_acc != nullptr);
+  if (!want_gH && !reduce_loss) return;
+  __shared__ float red[NT / 32][10];
+  float v[10];
+  v[0] = sa * gx; v[1] = say; v[2] = sa;
+  v[3] = sb * gx; v[4] = sby; v[5] = sb;
+  v[6] = sc * gx; v[7] = scy; v[8] = sc;
+  v[9] = lsum;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if ((k == 9) ? reduce_loss : want_gH) {
+      const float s = warp_sum(v[k]);
+      if (lane == 0) red[wrp][k] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    const int k = threadIdx.x;
+    if ((k == 9) ? reduce_loss : want_gH) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT / 32; ++q) s += red[q][k];
+      if (k == 9)
+        atomicAdd(tm.loss_acc + b, (double)s);
+      else
+        red_add(tm.grad_param + (size_t)b * 9 + k, s);
+    }
+  }
+}
+
+template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS>
+int launch(const FastArgs& a, int n, long long tiles, bool dense, cudaStream_t stream) {
+  dim3 grid((unsigned)tiles, (unsigned)n, 1);
+  // the dense profile exists for the S1 headline paths only (homography or flow parameterised)
+  constexpr bool kHasDense = (SAMPLER == DMH_S1) && (PASS == PASS_FWD ? LOSS == DMH_LOSS_NONE : LOSS == DMH_LOSS_MASKED_DIFF);
+  if constexpr (kHasDense) {
+    if (dense) {
+      warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1><<<grid, NT, 0, stream>>>(a);
+      return launched("warp_fast_kernel");
+    }
+  }
+  warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 0><<<grid, NT, 0, stream>>>(a);
+  return launched("warp_fast_kernel");
+}
+
+template <int SAMPLER, int PARAM, int PASS, int CT>
+int launch_l(const FastArgs& a, int n, long long tiles, int loss, bool dense, cudaStream_t stream) {
+  switch (loss) {
+    case DMH_LOSS_NONE:
+      if (PASS == PASS_FUSED) break;  // a fused pass without a loss has nothing to differentiate
+      return launch<SAMPLER, PARAM, PASS, CT, DMH_LOSS_NONE>(a, n, tiles, dense, stream);
+    case DMH_LOSS_MASKED_DIFF: return launch<SAMPLER, PARAM, PASS, CT, DMH_LOSS_MASKED_DIFF>(a, n, tiles, dense, stream);
+    case DMH_LOSS_DIFF_MASKED: return launch<SAMPLER, PARAM, PASS, CT, DMH_LOSS_DIFF_MASKED>(a, n, tiles, dense, stream);
+  }
+  return 1;
+}
+
+template <int SAMPLER, int PARAM, int PASS>
+int launch_c(const FastArgs& a, int n, long long tiles, int C, int loss, bool dense, cudaStream_t stream) {
+  if (C == 1) return launch_l<SAMPLER, PARAM, PASS, 1>(a, n, tiles, loss, dense, stream);
+  if (C == 3) return launch_l<SAMPLER, PARAM, PASS, 3>(a, n, tiles, loss, dense, stream);
+  return 1;
+}
+
+template <int SAMPLER, int PARAM>
+int launch_pass(const FastArgs& a, int n, long long tiles, int pass, int C, int loss, bool dense, cudaStream_t stream) {
+  switch (pass) {
+    case PASS_FWD: return launch_c<SAMPLER, PARAM, PASS_FWD>(a, n, tiles, C, loss, dense, stream);
+    case PASS_BWD: return launch_c<SAMPLER, PARAM, PASS_BWD>(a, n, tiles, C, loss, dense, stream);
+    case PASS_FUSED: return launch_c<SAMPLER, PARAM, PASS_FUSED>(a, n, tiles, C, loss, dense, stream);
+  }
+  return 1;
+}
+
+}  // namespace
+
+// Returns DMH_OK / DMH_ECUDA when it launched, 1 when the request is outside the fast path.
+int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) {
+  const dmh_warp_desc& d0 = d[0];
+  if (n > 2) return 1;
+  if (d0.C != 1 && d0.C != 3) return 1;
+  if (d0.sampler != DMH_S1 && d0.sampler != DMH_S3_BORDER) return 1;
+  if (d0.param_kind != DMH_PARAM_HOMOGRAPHY && d0.param_kind != DMH_PARAM_FLOW) return 1;
+  if ((long long)d0.C * d0.Hs * d0.Ws >= 2147483647LL || (long long)d0.C * d0.h * d0.w >= 2147483647LL) return 1;
+  FastArgs a;
+  const int loss = (d0.target != nullptr) ? d0.loss_form : DMH_LOSS_NONE;
+  bool dense = true;
+  for (int i = 0; i < n; ++i) {
+    const dmh_warp_desc& s = d[i];
+    if (pass == PASS_FWD)
+      dense = dense && s.out && s.valid && !s.soft_mask && loss == DMH_LOSS_NONE;
+    else
+      dense = dense && s.use_border_mask && !s.soft_mask && s.grad_src && s.grad_target && s.grad_param &&
+              !s.grad_soft_mask && !s.grad_out && (pass == PASS_BWD || s.loss_acc) && loss == DMH_LOSS_MASKED_DIFF;
+    if (s.start || s.flow_out || s.indices) return 1;
+    if (s.param_kind == DMH_PARAM_HOMOGRAPHY && s.divide != 1) return 1;
+    if (s.loss_form != d0.loss_form || s.start_x != d0.start_x || s.start_y != d0.start_y) return 1;
+    if (pass == PASS_FWD && !s.out && !s.valid && !(s.loss_form != DMH_LOSS_NONE && s.loss_acc)) return 1;
+    FastTerm& t = a.t[i];
+    t.src = s.src; t.param = s.param; t.target = s.target; t.soft_mask = s.soft_mask;
+    t.grad_out = s.grad_out; t.grad_loss = s.grad_loss; t.sample_weight = s.sample_weight;
+    t.out = s.out; t.valid = s.valid; t.loss_acc = s.loss_acc;
+    t.grad_src = s.grad_src; t.grad_target = s.grad_target; t.grad_param = s.grad_param;
+    t.grad_soft_mask = s.grad_soft_mask;
+    t.grad_loss_scale = s.grad_loss_scale;
+    t.use_border_mask = s.use_border_mask;
+  }
+  if (n == 1) a.t[1] = a.t[0];
+  a.B = d0.B; a.Hs = d0.Hs; a.Ws = d0.Ws; a.h = d0.h; a.w = d0.w;
+  a.sx = d0.start_x; a.sy = d0.start_y;
+  a.tiles_x = (d0.w + TW - 1) / TW;
+  a.tiles_y = (d0.h + TH - 1) / TH;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * d0.B;
+  if (tiles > 2147483647LL) return 1;
+  if (d0.sampler == DMH_S1) {
+    if (d0.param_kind == DMH_PARAM_HOMOGRAPHY)
+      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, dense, stream);
+    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense, stream);
+  }
+  if (d0.param_kind == DMH_PARAM_FLOW)
+    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense, stream);
+  return 1;
+}
+
+}  // namespace dmh

@@ -1,0 +1,42 @@
+// Internal interface between the general warp dispatcher (dmh_warp.cu) and the lean
+// specialisations (dmh_warp_fast.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dmhomo.h"
+
+namespace dmh {
+
+// The fields of dmh_warp_desc the lean kernels read, per term.
+struct FastTerm {
+  const float* src;
+  const float* param;
+  const float* target;
+  const float* soft_mask;
+  const float* grad_out;
+  const float* grad_loss;
+  const float* sample_weight;
+  float* out;
+  uint8_t* valid;
+  double* loss_acc;
+  float* grad_src;
+  float* grad_target;
+  float* grad_param;
+  float* grad_soft_mask;
+  float grad_loss_scale;
+  int use_border_mask;
+};
+
+struct FastArgs {
+  FastTerm t[2];
+  int B, Hs, Ws, h, w;
+  int tiles_x, tiles_y;
+  float sx, sy;
+};
+
+// pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it
+// launched, 1 when the request is outside the lean path (caller falls back to the general kernel).
+int warp_fast_try(const dmh_warp_desc* descs, int n, int pass, cudaStream_t stream);
+
+}  // namespace dmh
