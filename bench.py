@@ -393,7 +393,7 @@ def run_ours(args):
             alg_bytes = wl["bytes_per_px"] * st.pixels
             achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "warp_kernel<S1,HOMOGRAPHY,FUSED> (both directions, one launch)",
+                        "traffic": traffic, "kernel": "warp_fast_kernel<S1,HOMOGRAPHY,FUSED,C=%d,MASKED_DIFF,dense> (both directions, one launch)" % st.C,
                         "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -38,7 +38,7 @@ def ComputeErrFlow(src, dst, flow):
     """HEM/loss/losses.py:208-211 for one point: || dst - (src + flow[int(y), int(x)]) ||."""
     pts = torch.stack([src, dst], 0).view(1, 1, 2, 2)
     f = flow.unsqueeze(0)
-    return ops.eval_point_error(pts, f, f)[0]  # both directions see the same (src, flow): min is a no-op
+    return ops.eval_point_error(pts, f, None)[0]
 
 
 def compute_eval_results(data_batch, output_batch):

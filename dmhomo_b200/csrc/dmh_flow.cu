@@ -347,6 +347,10 @@ __global__ void eval_point_error_kernel(const float* __restrict__ pts, const flo
     float e[2];
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
+      if (dir == 1 && fb == nullptr) {  // single-direction query (ComputeErrFlow)
+        e[1] = e[0];
+        break;
+      }
       const float sx_ = dir ? p2x : p1x, sy_ = dir ? p2y : p1y, dx_ = dir ? p1x : p2x, dy_ = dir ? p1y : p2y;
       const float* fl = dir ? fb : ff;
       int iy = (int)sy_, ix = (int)sx_;          // int() truncation (losses.py:209)
@@ -494,7 +498,7 @@ extern "C" int dmh_flow_to_rgb(const float* flow, float* rgb, int B, int h, int 
 
 extern "C" int dmh_eval_point_error(const float* pts, const float* flow_f, const float* flow_b, float* err, int B,
                                     int P, int h, int w, void* stream) {
-  DMH_REQUIRE(pts && flow_f && flow_b && err, "eval_point_error: null pointer");
+  DMH_REQUIRE(pts && flow_f && err, "eval_point_error: null pointer");
   DMH_REQUIRE(B > 0 && P > 0 && h > 0 && w > 0, "eval_point_error: bad size");
   eval_point_error_kernel<<<(B + 63) / 64, 64, 0, as_stream(stream)>>>(pts, flow_f, flow_b, err, B, P, h, w);
   return launched("eval_point_error_kernel");

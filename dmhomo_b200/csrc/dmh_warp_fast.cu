@@ -18,6 +18,8 @@
 #include "dmh_sampler.cuh"
 #include "dmh_warp_fast.h"
 
+#include <cstdlib>
+
 namespace dmh {
 
 namespace {
@@ -27,6 +29,11 @@ constexpr int WX = 2, WY = 4, RPT = 16;
 constexpr int TW = 32 * WX, TH = WY * RPT;
 
 enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
+
+// default tuning (tools/tune.sh sweep, gpurun_out/tune*.txt): no software pipeline, L1 prefetch 3 rows
+// ahead, register budget for 4 resident CTAs/SM (C = 1) - the kernel is issue-bound, so occupancy wins
+constexpr int kTuneDense = 0 | 3 << 4 | 4 << 8;
+constexpr int kTuneGeneral = 0 | 3 << 4 | 2 << 8;
 
 // Explicit global-space accesses (the pinned bases below are opaque to the compiler, which would
 // otherwise fall back to generic-address atomics): ld.global.nc, st.global, red.global.add.
@@ -52,6 +59,7 @@ __device__ __forceinline__ T* pin(T* p) {
   asm volatile("" : "+l"(p));
   return p;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float rcp_fast(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -63,8 +71,12 @@ __device__ __forceinline__ float rcp_fast(float x) {
 //   forward            out + valid written, no soft mask
 //   backward / fused   border mask on, no soft mask, gradients to src, target and param all wanted,
 //                      loss accumulated (fused); no grad_soft_mask, no grad_out.
-template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS, int PROFILE>
-__global__ void __launch_bounds__(NT, 2) warp_fast_kernel(const __grid_constant__ FastArgs a) {
+// TUNE = PIPE | PF << 4 | MINB << 8: software-pipeline depth-2 on/off, L1 prefetch distance in rows (0 = off),
+// minimum resident CTAs per SM for the register allocator.
+template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS, int PROFILE, int TUNE>
+__global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const __grid_constant__ FastArgs a) {
+  constexpr bool kPipe = (TUNE & 1) != 0;
+  constexpr int kPF = (TUNE >> 4) & 15;
   constexpr bool kGrad = (PASS != PASS_FWD);
   constexpr bool kOut = (PASS != PASS_BWD);
   constexpr bool kLoss = (LOSS != DMH_LOSS_NONE);
@@ -135,135 +147,202 @@ __global__ void __launch_bounds__(NT, 2) warp_fast_kernel(const __grid_constant_
 #pragma unroll
   for (int c = 0; c < CT; ++c) pB[c] = pD[c] = 0.f;
 
-  if (col_live) {
-    unsigned po = (unsigned)(y_begin * w + x);
-    float yf = (float)y_begin;
-#pragma unroll 2
-    for (int y = y_begin; y < y_end; ++y, po += (unsigned)w, yf += 1.0f) {
-      const float gy = add_rn(yf, sy);
-      // ---- sampling coordinate ------------------------------------------------------------
-      float fx, fy, qx = 0.f, qy = 0.f, qT = 1.f;
-      if (PARAM == DMH_PARAM_FLOW) {
-        fx = ldg_f(flow, po);
-        fy = ldg_f(flow, po + plane_o);
-      } else {
-        // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
-        const float qX = add_rn(add_rn(h0x, mul_rn(hm[1], gy)), hm[2]);
-        const float qY = add_rn(add_rn(h3x, mul_rn(hm[4], gy)), hm[5]);
-        qT = add_rn(add_rn(h6x, mul_rn(hm[7], gy)), hm[8]);
-        if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
-        qx = div_rn(qX, qT);
-        qy = div_rn(qY, qT);
-        fx = sub_rn(qx, gx);
-        fy = sub_rn(qy, gy);
-      }
-      const float cx = add_rn(gx, fx), cy = add_rn(gy, fy);
+  // One row of this thread's column, split in two stages so that the loads of row r+1 are in
+  // flight while row r is blended, reduced and scattered (software pipeline, depth 2).
+  struct Row {
+    unsigned po;
+    int ia, ib, ic, id;
+    float ax0, ax1, ay0, ay1, gate_x, gate_y;
+    float m, soft, gy, qx, qy, qT;
+    bool m1;
+    float I[CT][4], tv[CT], go[CT];
+  };
 
-      // ---- M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h ------------
-      float m = 1.f;
-      bool m1 = true;
-      if (want_mask) {
-        const float mx = add_rn(fx, xf), my = add_rn(fy, yf);
-        m1 = (mx >= 0.f) && (mx <= wf) && (my >= 0.f) && (my <= hf);
-        if (has_valid) stg_u8(valid, po, m1 ? 1 : 0);
-        if (use_border) m = m1 ? 1.f : 0.f;
-      }
-      if (!kDense && soft) m = mul_rn(m, ldg_f(soft, po));
-
-      // ---- taps ---------------------------------------------------------------------------
-      Taps tp;
-      int x0, y0, x1, y1;
-      make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
-
-      float gcx = 0.f, gcy = 0.f, gmask = 0.f;
-      float cA[CT], cB[CT], cC[CT], cD[CT];
-      bool any_go = false;
+  // stage 1: coordinate, mask, taps, issue every load of the row
+  auto issue = [&](int y, Row& r) {
+    const float yf = (float)y;
+    const float gy = add_rn(yf, sy);
+    const unsigned po = (unsigned)(y * w + x);
+    r.po = po;
+    r.gy = gy;
+    float fx, fy;
+    r.qx = r.qy = 0.f;
+    r.qT = 1.f;
+    if (PARAM == DMH_PARAM_FLOW) {
+      fx = ldg_f(flow, po);
+      fy = ldg_f(flow, po + plane_o);
+    } else {
+      // (h0*x + h1*y) + h2, every product and sum rounded separately (App. A.2)
+      const float qX = add_rn(add_rn(h0x, mul_rn(hm[1], gy)), hm[2]);
+      const float qY = add_rn(add_rn(h3x, mul_rn(hm[4], gy)), hm[5]);
+      float qT = add_rn(add_rn(h6x, mul_rn(hm[7], gy)), hm[8]);
+      if (!(fabsf(qT) >= 1e-7f)) qT = add_rn(qT, 1e-6f);
+      r.qx = div_rn(qX, qT);
+      r.qy = div_rn(qY, qT);
+      r.qT = qT;
+      fx = sub_rn(r.qx, gx);
+      fy = sub_rn(r.qy, gy);
+    }
+    const float cx = add_rn(gx, fx), cy = add_rn(gy, fy);
+    // M1 validity mask on fl(flow + grid) (no start), inclusive bounds w, h
+    r.m = 1.f;
+    r.m1 = true;
+    if (want_mask) {
+      const float mx = add_rn(fx, xf), my = add_rn(fy, yf);
+      r.m1 = (mx >= 0.f) && (mx <= wf) && (my >= 0.f) && (my <= hf);
+      if (has_valid) stg_u8(valid, po, r.m1 ? 1 : 0);
+      if (use_border) r.m = r.m1 ? 1.f : 0.f;
+    }
+    r.soft = (!kDense && soft) ? ldg_f(soft, po) : 1.f;
+    Taps tp;
+    int x0, y0, x1, y1;
+    make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
+    r.ia = tp.ia; r.ib = tp.ib; r.ic = tp.ic; r.id = tp.id;
+    r.ax0 = tp.ax0; r.ax1 = tp.ax1; r.ay0 = tp.ay0; r.ay1 = tp.ay1;
+    r.gate_x = tp.gate_x; r.gate_y = tp.gate_y;
+    if (kPF > 0) {
+      // pull the lines rows kPF ahead will need into L1 now: the target row and (assuming the
+      // column keeps marching down the source) the bottom tap row
+      const unsigned pt = min(po + (unsigned)(kPF * w), plane_o - 1);
+      const unsigned ps = min((unsigned)(tp.ib + kPF * Ws), plane_s - 1);
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        const unsigned cs = (unsigned)c * plane_s, oo = po + (unsigned)c * plane_o;
-        const float Ia = ldg_f(src, cs + tp.ia), Ib = ldg_f(src, cs + tp.ib);
-        const float Ic = ldg_f(src, cs + tp.ic), Id = ldg_f(src, cs + tp.id);
-        const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
-        if (has_out) stg_f(out, oo, wv);
-        float go = 0.f;  // dL/d(out)
-        if (!kDense && PASS == PASS_BWD && gout) go = ldg_f(gout, oo);
-        if (kLoss) {
-          const float tv = ldg_f(tgt, oo);
-          float u, gm;
-          if (LOSS == DMH_LOSS_MASKED_DIFF) {
-            u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));   // |m*t - m*w|
-            if (kOut) lsum += fabsf(u);
-            gm = gscale * m;                            // d/dt = +gm*sign(u), d/dw = -gm*sign(u)
-          } else {
-            u = sub_rn(tv, wv);                         // m*|w - t|  (same sign convention: u = t - w)
-            if (kOut) lsum += m * fabsf(u);
-            gm = gscale * m;
-          }
-          if (kGrad) {
-            // gt = gm * sign(u): flip gm's sign bit with u's, zero where u == 0
-            float gt = __int_as_float(__float_as_int(gm) ^ (__float_as_int(u) & 0x80000000));
-            gt = (u == 0.f) ? 0.f : gt;
-            go -= gt;
-            if (has_gtgt && gt != 0.f) red_f(gtgt, oo, gt);
-            if (has_gsoft) {
-              const float sg = __int_as_float(__float_as_int(gscale) ^ (__float_as_int(u) & 0x80000000));
-              gmask += (u == 0.f) ? 0.f : ((LOSS == DMH_LOSS_MASKED_DIFF) ? sg * (tv - wv) : gscale * fabsf(u));
-            }
-          }
+        if (kLoss) prefetch_l1(tgt + ((unsigned)c * plane_o + pt));
+        prefetch_l1(src + ((unsigned)c * plane_s + ps));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const unsigned cs = (unsigned)c * plane_s, oo = po + (unsigned)c * plane_o;
+      r.I[c][0] = ldg_f(src, cs + tp.ia);
+      r.I[c][1] = ldg_f(src, cs + tp.ib);
+      r.I[c][2] = ldg_f(src, cs + tp.ic);
+      r.I[c][3] = ldg_f(src, cs + tp.id);
+      r.tv[c] = kLoss ? ldg_f(tgt, oo) : 0.f;
+      r.go[c] = (!kDense && PASS == PASS_BWD && gout) ? ldg_f(gout, oo) : 0.f;
+    }
+  };
+
+  // stage 2: blend, loss, gradients, scatter
+  auto consume = [&](const Row& r) {
+    const unsigned po = r.po;
+    const float m = (!kDense && soft) ? mul_rn(r.m, r.soft) : r.m;
+    Taps tp;
+    tp.ax0 = r.ax0; tp.ax1 = r.ax1; tp.ay0 = r.ay0; tp.ay1 = r.ay1;
+    // S1: wa=(x1f-x)(y1f-y) wb=(x1f-x)(y-y0f) wc=(x-x0f)(y1f-y) wd=(x-x0f)(y-y0f); S3: the same products
+    tp.wa = mul_rn(r.ax1, r.ay1);
+    tp.wb = mul_rn(r.ax1, r.ay0);
+    tp.wc = mul_rn(r.ax0, r.ay1);
+    tp.wd = mul_rn(r.ax0, r.ay0);
+    float gcx = 0.f, gcy = 0.f, gmask = 0.f;
+    float cA[CT], cB[CT], cC[CT], cD[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const unsigned oo = po + (unsigned)c * plane_o;
+      const float Ia = r.I[c][0], Ib = r.I[c][1], Ic = r.I[c][2], Id = r.I[c][3];
+      const float wv = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
+      if (has_out) stg_f(out, oo, wv);
+      float go = r.go[c];  // dL/d(out)
+      if (kLoss) {
+        const float tv = r.tv[c];
+        float u;
+        if (LOSS == DMH_LOSS_MASKED_DIFF) {
+          u = sub_rn(mul_rn(m, tv), mul_rn(m, wv));   // |m*t - m*w|
+          if (kOut) lsum += fabsf(u);
+        } else {
+          u = sub_rn(tv, wv);                         // m*|w - t|  (sign convention: u = t - w)
+          if (kOut) lsum += m * fabsf(u);
         }
         if (kGrad) {
-          cA[c] = tp.wa * go; cB[c] = tp.wb * go; cC[c] = tp.wc * go; cD[c] = tp.wd * go;
-          any_go = any_go || (go != 0.f);
-          // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
-          gcx = fmaf(go, fmaf(tp.ay1, Ic - Ia, tp.ay0 * (Id - Ib)), gcx);
-          gcy = fmaf(go, fmaf(tp.ax1, Ib - Ia, tp.ax0 * (Id - Ic)), gcy);
-        }
-      }
-
-      if (kGrad && has_gsrc && any_go) {
-        if (p_ib >= 0) {
-          if (p_ib == tp.ia && p_id == tp.ic) {  // previous bottom taps == this row's top taps
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-              cA[c] += pB[c];
-              cC[c] += pD[c];
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-              red_f(gsrc, (unsigned)c * plane_s + p_ib, pB[c]);
-              red_f(gsrc, (unsigned)c * plane_s + p_id, pD[c]);
-            }
+          // d/dt = +gm*sign(u), d/dw = -gm*sign(u): flip gm's sign bit with u's, zero where u == 0
+          const float gm = gscale * m;
+          float gt = __int_as_float(__float_as_int(gm) ^ (__float_as_int(u) & 0x80000000));
+          gt = (u == 0.f) ? 0.f : gt;
+          go -= gt;
+          if (has_gtgt) red_f(gtgt, oo, gt);
+          if (has_gsoft) {
+            const float sg = __int_as_float(__float_as_int(gscale) ^ (__float_as_int(u) & 0x80000000));
+            gmask += (u == 0.f) ? 0.f : ((LOSS == DMH_LOSS_MASKED_DIFF) ? sg * (tv - wv) : gscale * fabsf(u));
           }
         }
+      }
+      if (kGrad) {
+        cA[c] = tp.wa * go; cB[c] = tp.wb * go; cC[c] = tp.wc * go; cD[c] = tp.wd * go;
+        // d out / d cx = ay1*(Ic-Ia) + ay0*(Id-Ib);  d out / d cy = ax1*(Ib-Ia) + ax0*(Id-Ic)
+        gcx = fmaf(go, fmaf(r.ay1, Ic - Ia, r.ay0 * (Id - Ib)), gcx);
+        gcy = fmaf(go, fmaf(r.ax1, Ib - Ia, r.ax0 * (Id - Ic)), gcy);
+      }
+    }
+
+    if (kGrad && has_gsrc) {
+      // The previous row's bottom taps (pB at p_ib, pD at p_id) either coincide with this row's top
+      // taps (any near-rigid warp: almost always) and ride along in registers, or are flushed now.
+      // Rows whose upstream gradient is exactly zero (masked out) still post their (zero) top taps:
+      // one uniform code path is cheaper than the divergence bookkeeping that would skip them.
+      const bool same = (p_ib == r.ia) && (p_id == r.ic);
+      if (!same && p_ib >= 0) {
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-          red_f(gsrc, (unsigned)c * plane_s + tp.ia, cA[c]);
-          red_f(gsrc, (unsigned)c * plane_s + tp.ic, cC[c]);
-          pB[c] = cB[c];
-          pD[c] = cD[c];
+          red_f(gsrc, (unsigned)c * plane_s + (unsigned)p_ib, pB[c]);
+          red_f(gsrc, (unsigned)c * plane_s + (unsigned)p_id, pD[c]);
         }
-        p_ib = tp.ib;
-        p_id = tp.id;
       }
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const unsigned cs = (unsigned)c * plane_s;
+        red_f(gsrc, cs + (unsigned)r.ia, cA[c] + (same ? pB[c] : 0.f));
+        red_f(gsrc, cs + (unsigned)r.ic, cC[c] + (same ? pD[c] : 0.f));
+        pB[c] = cB[c];
+        pD[c] = cD[c];
+      }
+      p_ib = r.ib;
+      p_id = r.id;
+    }
 
-      if (kGrad) {
-        gcx *= tp.gate_x;
-        gcy *= tp.gate_y;
-        if (has_gsoft) stg_f(gsoft, po, (use_border && !m1) ? 0.f : gmask);
-        if (has_gflow) {
-          stg_f(gflow, po, gcx);
-          stg_f(gflow, po + plane_o, gcy);
-        }
-        if (want_gH) {
-          // flow = q/T' - g  =>  dL/dX = gcx/T', dL/dY = gcy/T', dL/dT = -(gcx*X + gcy*Y)/T'^2
-          const float rT = rcp_fast(qT);
-          const float ga = gcx * rT, gb = gcy * rT;
-          const float gc = -fmaf(ga, qx, gb * qy);
-          sa += ga; say = fmaf(ga, gy, say);
-          sb += gb; sby = fmaf(gb, gy, sby);
-          sc += gc; scy = fmaf(gc, gy, scy);
-        }
+    if (kGrad) {
+      gcx *= r.gate_x;
+      gcy *= r.gate_y;
+      if (has_gsoft) stg_f(gsoft, po, (use_border && !r.m1) ? 0.f : gmask);
+      if (has_gflow) {
+        stg_f(gflow, po, gcx);
+        stg_f(gflow, po + plane_o, gcy);
+      }
+      if (want_gH) {
+        // flow = q/T' - g  =>  dL/dX = gcx/T', dL/dY = gcy/T', dL/dT = -(gcx*X + gcy*Y)/T'^2
+        const float rT = rcp_fast(r.qT);
+        const float ga = gcx * rT, gb = gcy * rT;
+        const float gc = -fmaf(ga, r.qx, gb * r.qy);
+        sa += ga; say = fmaf(ga, r.gy, say);
+        sb += gb; sby = fmaf(gb, r.gy, sby);
+        sc += gc; scy = fmaf(gc, r.gy, scy);
+      }
+    }
+  };
+
+  if (col_live && y_begin < y_end) {
+    if (kPipe) {
+      Row r0, r1;
+      issue(y_begin, r0);
+      int y = y_begin;
+      // depth-2 pipeline, unrolled by two so that the row contexts never move between registers
+      for (; y + 2 < y_end; y += 2) {
+        issue(y + 1, r1);
+        consume(r0);
+        issue(y + 2, r0);
+        consume(r1);
+      }
+      if (y + 1 < y_end) {
+        issue(y + 1, r1);
+        consume(r0);
+        consume(r1);
+      } else {
+        consume(r0);
+      }
+    } else {
+      for (int y = y_begin; y < y_end; ++y) {
+        Row r;
+        issue(y, r);
+        consume(r);
       }
     }
     if (kGrad && has_gsrc && p_ib >= 0) {
@@ -313,11 +392,22 @@ int launch(const FastArgs& a, int n, long long tiles, bool dense, cudaStream_t s
   constexpr bool kHasDense = (SAMPLER == DMH_S1) && (PASS == PASS_FWD ? LOSS == DMH_LOSS_NONE : LOSS == DMH_LOSS_MASKED_DIFF);
   if constexpr (kHasDense) {
     if (dense) {
-      warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1><<<grid, NT, 0, stream>>>(a);
+#ifdef DMH_TUNE_BUILD
+      if (PASS == PASS_FUSED && CT == 1 && PARAM == DMH_PARAM_HOMOGRAPHY) {
+        static const int tune = getenv("DMH_TUNE") ? atoi(getenv("DMH_TUNE")) : 0;
+        switch (tune) {
+#define DMH_T(P, F, M) case (P | F << 4 | M << 8): warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (P | F << 4 | M << 8)><<<grid, NT, 0, stream>>>(a); return launched("warp_fast_kernel");
+          DMH_T(0, 0, 3) DMH_T(0, 2, 3) DMH_T(0, 3, 3) DMH_T(0, 4, 3) DMH_T(1, 0, 3) DMH_T(1, 3, 3) DMH_T(1, 3, 2) DMH_T(0, 3, 4) DMH_T(0, 0, 4) DMH_T(0, 3, 2)
+#undef DMH_T
+          default: break;
+        }
+      }
+#endif
+      warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (CT == 1) ? kTuneDense : kTuneGeneral><<<grid, NT, 0, stream>>>(a);
       return launched("warp_fast_kernel");
     }
   }
-  warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 0><<<grid, NT, 0, stream>>>(a);
+  warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 0, kTuneGeneral><<<grid, NT, 0, stream>>>(a);
   return launched("warp_fast_kernel");
 }
 

@@ -624,9 +624,10 @@ def warp_perspective(img, H, dsize, channels_last=False):
 
 
 def eval_point_error(pts, flow_f, flow_b):
-    """compute_eval_results() (HEM/loss/losses.py:263-296): pts (B,P,2,2), flows (B,h,w,2) -> (B,)."""
+    """compute_eval_results() (HEM/loss/losses.py:263-296): pts (B,P,2,2), flows (B,h,w,2) -> (B,).
+    With flow_b=None only the forward error is returned (ComputeErrFlow, losses.py:208-211)."""
     dev = _cuda(pts, flow_f, flow_b)
-    p, ff, fb = _f32(pts), _f32(flow_f), _f32(flow_b)
+    p, ff, fb = _f32(pts), _f32(flow_f), _f32(flow_b)  # flow_b None: forward direction only
     B, P = p.shape[:2]
     _, h, w, _ = ff.shape
     err = torch.empty(B, device=dev, dtype=torch.float32)

@@ -216,7 +216,7 @@ DMH_API int dmh_warp_perspective(const float* src, const double* H, float* dst, 
 /* --- evaluation metric (A18) --------------------------------------------------------------- */
 /* compute_eval_results(): per sample mean over P points of min(err(p1->p2, flow_f), err(p2->p1, flow_b)),
  * err = ||dst - (src + flow[int(y), int(x)])||.  HEM/loss/losses.py:208-211, 263-296.
- * pts (B,P,2,2); flows (B,h,w,2); err (B). */
+ * pts (B,P,2,2); flows (B,h,w,2); err (B).  flow_b may be null: forward direction only (ComputeErrFlow). */
 DMH_API int dmh_eval_point_error(const float* pts, const float* flow_f, const float* flow_b, float* err, int B,
                          int P, int h, int w, void* stream);
 
