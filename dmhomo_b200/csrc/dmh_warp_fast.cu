@@ -392,6 +392,15 @@ int launch(const FastArgs& a, int n, long long tiles, bool dense, cudaStream_t s
   constexpr bool kHasDense = (SAMPLER == DMH_S1) && (PASS == PASS_FWD ? LOSS == DMH_LOSS_NONE : LOSS == DMH_LOSS_MASKED_DIFF);
   if constexpr (kHasDense) {
     if (dense) {
+      if constexpr (PASS != PASS_BWD) {
+        // Measured (profiles/r1_tune_sweeps.txt): the paired kernel executes 21 % fewer instructions but its
+        // register footprint halves the resident warps and it ends up ~3 % slower; opt-in until it is staged.
+        static const bool use_pair = getenv("DMH_PAIR") != nullptr;
+        if (use_pair) {
+          FastArgs ap = a;
+          return warp_pair_launch(ap, n, tiles, PARAM, PASS, CT, stream);
+        }
+      }
 #ifdef DMH_TUNE_BUILD
       if (PASS == PASS_FUSED && CT == 1 && PARAM == DMH_PARAM_HOMOGRAPHY) {
         static const int tune = getenv("DMH_TUNE") ? atoi(getenv("DMH_TUNE")) : 0;

@@ -33,10 +33,15 @@ struct FastArgs {
   int B, Hs, Ws, h, w;
   int tiles_x, tiles_y;
   float sx, sy;
+  // opaque identities for the packed (f32x2) kernels, see dmh_warp_pair.cu
+  float one, neg_zero, minus_one;
 };
 
 // pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it
 // launched, 1 when the request is outside the lean path (caller falls back to the general kernel).
 int warp_fast_try(const dmh_warp_desc* descs, int n, int pass, cudaStream_t stream);
+
+// Paired (two rows per thread, packed fp32) form of the dense S1 forward / fused launches.
+int warp_pair_launch(FastArgs& a, int n, long long tiles, int param_kind, int pass, int C, cudaStream_t stream);
 
 }  // namespace dmh
