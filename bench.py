@@ -189,10 +189,11 @@ class PairStep:
             img1 = torch.rand(B, C, h, w, generator=gen, device=dev).requires_grad_(True)
             img2 = torch.rand(B, C, h, w, generator=gen, device=dev).requires_grad_(True)
             if workload == "cfg2":
-                par = ((torch.rand(2 * B, 8, generator=gen, device=dev) * 2 - 1) * 4.0).requires_grad_(True)
+                par = tuple(((torch.rand(B, 8, generator=gen, device=dev) * 2 - 1) * 4.0).requires_grad_(True)
+                            for _ in range(2))
             else:
                 par = ((torch.rand(2 * B, 4, 2, generator=gen, device=dev) * 2 - 1) * 32.0).requires_grad_(True)
-            self.sets.append((img1, img2, par))
+            self.sets.append((img1, img2) + (par if isinstance(par, tuple) else (par,)))
         self.basis = hem_utils.gen_basis(h, w).to(dev) if workload == "cfg2" else None
         self.src2 = synth.corner_points(2 * B, h, w, dev)
         self.pixels = 2 * B * h * w
@@ -201,16 +202,17 @@ class PairStep:
 
     def forward_backward(self, k, ev=None):
         ops = self.ops
-        img1, img2, par = self.sets[k]
+        img1, img2, *par = self.sets[k]
         B, h, w = self.B, self.h, self.w
         if self.workload == "cfg2":
-            off = ops.basis_corner_offsets(self.basis, par, h, w)
+            # 8 basis weights -> corner offsets -> DLT, both directions, one launch
+            Hf, Hb = ops.basis_homography(self.basis, h, w, par[0], par[1])
         else:
-            off = par
-        H = ops.dlt4(self.src2, self.src2 + off)
+            H = ops.dlt4(self.src2, self.src2 + par[0])
+            Hf, Hb = H[:B], H[B:]
         if ev is not None:
             ev[0].record()
-        loss = ops.warp_loss([ops.WarpTerm(img2, img1, H[:B]), ops.WarpTerm(img1, img2, H[B:])],
+        loss = ops.warp_loss([ops.WarpTerm(img2, img1, Hf), ops.WarpTerm(img1, img2, Hb)],
                              kind=ops.PARAM_HOMOGRAPHY, sampler=ops.S1, loss_form=ops.LOSS_MASKED_DIFF,
                              border_mask=True, fused=True)
         if ev is not None:

@@ -83,6 +83,8 @@ SIGNATURES = {
     "dmh_basis_combine_backward": [_fp, _fp, _fp, _i, _i, _i, _fp],
     "dmh_basis_corner_offsets": [_fp, _fp, _fp, _i, _i, _i, _fp],
     "dmh_basis_corner_offsets_backward": [_fp, _fp, _fp, _i, _i, _i, _fp],
+    "dmh_basis_homography_forward": [_fp, C.POINTER(_fp), C.POINTER(_fp), _i, _i, _i, _i, _fp],
+    "dmh_basis_homography_backward": [_fp, C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_fp), _i, _i, _i, _i, _fp],
     "dmh_border_mask": [_fp, _fp, _fp, _i, _i, _i, _fp],
     "dmh_zero_border_mask": [_fp, _fp, _i, _i, _i, _f, _fp],
     "dmh_l1_sum": [_fp, _fp, _i64, _fp, _fp],

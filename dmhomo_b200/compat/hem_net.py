@@ -6,7 +6,7 @@ import torch
 from .. import ops
 from .hem_utils import gen_basis  # noqa: F401  (net.py:118-154 duplicates utils.gen_basis)
 
-__all__ = ["DLT_solve", "gen_basis", "basis_flow"]
+__all__ = ["DLT_solve", "gen_basis", "basis_flow", "basis_homography"]
 
 
 def DLT_solve(src_p, off_set):
@@ -28,3 +28,10 @@ def DLT_solve(src_p, off_set):
 def basis_flow(basis, weight, h, w):
     """(basis * weight).sum(1).reshape(bs, 2, h, w)  (HEM/model/net.py:808-809, 814-815)."""
     return ops.basis_combine(basis, weight, h, w)
+
+
+def basis_homography(basis, h, w, *weights):
+    """8 basis weights -> basis flow at the 4 image corners -> 4-point DLT -> H (B,3,3), for up to four
+    weight sets in one launch: the "8-coefficient basis-flow prediction -> 8x8 DLT solve" entry of the path
+    (net.py:808-815 sampled at the corners, then utils.py:55-101)."""
+    return ops.basis_homography(basis, h, w, *weights)

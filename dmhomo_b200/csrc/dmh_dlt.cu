@@ -161,6 +161,103 @@ __global__ void basis_corner_bwd_kernel(const float* __restrict__ basis, const f
   red_add(g_w + t, acc);
 }
 
+
+// ---- fused: 8 basis weights -> corner offsets -> 4-point DLT (cfg 2 prologue), one warp per sample ----
+// Lane j < 8 owns offset j = (corner j/2, xy j&1) exactly as basis_corner_fwd_kernel computes it (sequential,
+// separately rounded), then the warp assembles and solves the 8x8 system like dlt4_fwd_kernel.  Up to four
+// weight sets (e.g. forward / backward direction) share one launch.
+struct BasisHArgs {
+  const float* weight[4];
+  const float* grad_H[4];
+  float* H[4];
+  float* grad_weight[4];
+};
+
+__device__ __forceinline__ void corner_xy(int c, int h, int w, float& x, float& y) {
+  x = (c & 1) ? (float)(w - 1) : 0.f;
+  y = (c >> 1) ? (float)(h - 1) : 0.f;
+}
+
+__global__ void __launch_bounds__(128) basis_h_fwd_kernel(const float* __restrict__ basis, BasisHArgs args, int n_sets,
+                                                          int B, int h, int w) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= n_sets * B) return;  // warp-uniform
+  const int set = n / B, b = n - set * B;
+  const int lane = threadIdx.x & 31, j = lane & 7;
+  const float* wp = args.weight[set] + (size_t)b * 8;
+  const int c = j >> 1, xy = j & 1;
+  const int py = (c >> 1) ? h - 1 : 0, px = (c & 1) ? w - 1 : 0;
+  const size_t plane = (size_t)h * w, po = (size_t)py * w + px;
+  float off = mul_rn(__ldg(basis + (size_t)xy * plane + po), __ldg(wp));
+  for (int k = 1; k < 8; ++k) off = add_rn(off, mul_rn(__ldg(basis + (size_t)(2 * k + xy) * plane + po), __ldg(wp + k)));
+  // row r = lane & 7 of the system needs (x, y, u, v) of point i = r / 2: u, v = corner + offset
+  const int i = j >> 1;
+  float x, y;
+  corner_xy(i, h, w, x, y);
+  const float ox = __shfl_sync(0xffffffffu, off, 2 * i), oy = __shfl_sync(0xffffffffu, off, 2 * i + 1);
+  const float u = add_rn(x, ox), v = add_rn(y, oy);
+  double m[9], sol[8];
+  dlt_row(j, x, y, u, v, m);
+  solve8_warp(m, lane, sol);
+  float* H = args.H[set] + (size_t)b * 9;
+  if (lane < 8) H[lane] = (float)sol[lane];
+  if (lane == 8) H[8] = 1.0f;
+}
+
+// grad_H -> grad_weight (written): adjoint DLT solve (as dlt4_bwd_kernel), then the transpose of the corner
+// sampling: g_w[k] = sum_{corner, xy} g_off[corner, xy] * basis[k, xy, corner].
+__global__ void __launch_bounds__(128) basis_h_bwd_kernel(const float* __restrict__ basis, BasisHArgs args, int n_sets,
+                                                          int B, int h, int w) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= n_sets * B) return;
+  const int set = n / B, b = n - set * B;
+  const int lane = threadIdx.x & 31, r = lane & 7;
+  const float* H = args.H[set] + (size_t)b * 9;
+  // destination points u, v = corner + offset are recovered from H itself: dst_i = H * src_i (exact up to the
+  // solve's rounding, far below the gradient tolerance)
+  float xs[4], ys[4], us[4], vs[4];
+  const float h0 = __ldg(H), h1 = __ldg(H + 1), h2 = __ldg(H + 2), h3 = __ldg(H + 3), h4 = __ldg(H + 4), h5 = __ldg(H + 5),
+              h6 = __ldg(H + 6), h7 = __ldg(H + 7);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    corner_xy(i, h, w, xs[i], ys[i]);
+    const float T = h6 * xs[i] + h7 * ys[i] + 1.0f;
+    us[i] = (h0 * xs[i] + h1 * ys[i] + h2) / T;
+    vs[i] = (h3 * xs[i] + h4 * ys[i] + h5) / T;
+  }
+  double m[9];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    double row[9];
+    dlt_row(jj, xs[jj >> 1], ys[jj >> 1], us[jj >> 1], vs[jj >> 1], row);
+    m[jj] = row[r];
+  }
+  m[8] = (double)__ldg(args.grad_H[set] + (size_t)b * 9 + r);
+  double z[8];
+  solve8_warp(m, lane, z);
+  // g_off[2i] = z[2i] * s_i, g_off[2i+1] = z[2i+1] * s_i, s_i = 1 + x_i h6 + y_i h7
+  float goff[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double s = 1.0 + (double)xs[i] * h6 + (double)ys[i] * h7;
+    goff[2 * i] = (float)(z[2 * i] * s);
+    goff[2 * i + 1] = (float)(z[2 * i + 1] * s);
+  }
+  if (lane < 8) {
+    const int k = lane;
+    const size_t plane = (size_t)h * w;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int py = (c >> 1) ? h - 1 : 0, px = (c & 1) ? w - 1 : 0;
+      const size_t po = (size_t)py * w + px;
+      acc += goff[2 * c] * __ldg(basis + (size_t)(2 * k) * plane + po);
+      acc += goff[2 * c + 1] * __ldg(basis + (size_t)(2 * k + 1) * plane + po);
+    }
+    args.grad_weight[set][(size_t)b * 8 + k] = acc;
+  }
+}
+
 }  // namespace dmh
 
 extern "C" int dmh_dlt4_forward(const float* src, const float* dst, float* H, int N, void* stream) {
@@ -193,4 +290,35 @@ extern "C" int dmh_basis_corner_offsets_backward(const float* basis, const float
   dmh::basis_corner_bwd_kernel<<<(B * 8 + 127) / 128, 128, 0, dmh::as_stream(stream)>>>(basis, grad_offsets,
                                                                                       grad_weight, B, h, w);
   return dmh::launched("basis_corner_bwd_kernel");
+}
+
+extern "C" int dmh_basis_homography_forward(const float* basis, const float* const* weights, float* const* H, int n_sets,
+                                            int B, int h, int w, void* stream) {
+  DMH_REQUIRE(basis && weights && H, "basis_homography_forward: null pointer");
+  DMH_REQUIRE(n_sets >= 1 && n_sets <= 4 && B > 0 && h > 1 && w > 1, "basis_homography_forward: bad size");
+  dmh::BasisHArgs a = {};
+  for (int i = 0; i < n_sets; ++i) {
+    DMH_REQUIRE(weights[i] && H[i], "basis_homography_forward: null pointer in set %d", i);
+    a.weight[i] = weights[i];
+    a.H[i] = H[i];
+  }
+  const int N = n_sets * B;
+  dmh::basis_h_fwd_kernel<<<(N + 3) / 4, 128, 0, dmh::as_stream(stream)>>>(basis, a, n_sets, B, h, w);
+  return dmh::launched("basis_h_fwd_kernel");
+}
+
+extern "C" int dmh_basis_homography_backward(const float* basis, const float* const* H, const float* const* grad_H,
+                                             float* const* grad_weight, int n_sets, int B, int h, int w, void* stream) {
+  DMH_REQUIRE(basis && H && grad_H && grad_weight, "basis_homography_backward: null pointer");
+  DMH_REQUIRE(n_sets >= 1 && n_sets <= 4 && B > 0 && h > 1 && w > 1, "basis_homography_backward: bad size");
+  dmh::BasisHArgs a = {};
+  for (int i = 0; i < n_sets; ++i) {
+    DMH_REQUIRE(H[i] && grad_H[i] && grad_weight[i], "basis_homography_backward: null pointer in set %d", i);
+    a.H[i] = const_cast<float*>(H[i]);
+    a.grad_H[i] = grad_H[i];
+    a.grad_weight[i] = grad_weight[i];
+  }
+  const int N = n_sets * B;
+  dmh::basis_h_bwd_kernel<<<(N + 3) / 4, 128, 0, dmh::as_stream(stream)>>>(basis, a, n_sets, B, h, w);
+  return dmh::launched("basis_h_bwd_kernel");
 }

@@ -15,7 +15,7 @@ from ._lib import (LOSS_DIFF_MASKED, LOSS_MASKED_DIFF, LOSS_NONE, PARAM_BASIS8, 
 __all__ = [
     "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8",
     "LOSS_NONE", "LOSS_MASKED_DIFF", "LOSS_DIFF_MASKED", "dlt4", "homography_to_flow", "homography_to_flow_f64",
-    "basis_combine", "basis_corner_offsets", "warp", "warp_loss", "WarpTerm", "border_mask", "zero_border_mask",
+    "basis_combine", "basis_corner_offsets", "basis_homography", "warp", "warp_loss", "WarpTerm", "border_mask", "zero_border_mask",
     "l1_loss", "flow_to_rgb", "warp_perspective", "eval_point_error", "flow_to_homography_ls",
 ]
 
@@ -271,6 +271,55 @@ def basis_corner_offsets(basis, weight, h, w):
     if basis.numel() != 16 * h * w:
         raise ValueError("basis must hold 8*2*h*w values")
     return _BasisCorners.apply(basis, weight, int(h), int(w))
+
+
+class _BasisHomography(torch.autograd.Function):
+    """weights (B,8) x n_sets -> H (B,3,3) x n_sets through corner offsets and the 4-point DLT: one launch."""
+
+    @staticmethod
+    def forward(ctx, basis, h, w, *weights):
+        dev = _cuda(basis, *weights)
+        bc = _f32(basis)
+        ws = [_f32(t).reshape(-1, 8) for t in weights]
+        B = ws[0].shape[0]
+        if any(t.shape[0] != B for t in ws) or not 1 <= len(ws) <= 4:
+            raise ValueError("basis_homography: 1..4 weight sets of equal batch size")
+        Hs = [torch.empty(B, 3, 3, device=dev, dtype=torch.float32) for _ in ws]
+        n = len(ws)
+        wp = (C.c_void_p * n)(*[t.data_ptr() for t in ws])
+        hp = (C.c_void_p * n)(*[t.data_ptr() for t in Hs])
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_homography_forward(_p(bc), wp, hp, n, B, h, w, _stream(dev)),
+                    "basis_homography_forward")
+        ctx.save_for_backward(bc, *Hs)
+        ctx.cfg = (B, h, w, [t.shape for t in weights])
+        return tuple(Hs)
+
+    @staticmethod
+    def backward(ctx, *gHs):
+        bc, *Hs = ctx.saved_tensors
+        B, h, w, shapes = ctx.cfg
+        dev = bc.device
+        n = len(Hs)
+        gH = [_f32(g) if g is not None else torch.zeros_like(Hs[i]) for i, g in enumerate(gHs)]
+        gw = [torch.empty(B, 8, device=dev, dtype=torch.float32) for _ in range(n)]
+        hp = (C.c_void_p * n)(*[t.data_ptr() for t in Hs])
+        gp = (C.c_void_p * n)(*[t.data_ptr() for t in gH])
+        wp = (C.c_void_p * n)(*[t.data_ptr() for t in gw])
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_basis_homography_backward(_p(bc), hp, gp, wp, n, B, h, w, _stream(dev)),
+                    "basis_homography_backward")
+        return (None, None, None) + tuple(g.view(s) for g, s in zip(gw, shapes))
+
+
+def basis_homography(basis, h, w, *weights):
+    """8 basis weights -> basis flow at the 4 image corners -> 4-point DLT -> H, for up to four weight sets
+    (e.g. forward and backward direction) in ONE launch.  Equivalent to
+    dlt4(corners, corners + basis_corner_offsets(basis, w_i, h, w)) per set (cfg 2's "8-basis flow -> DLT")."""
+    if basis.numel() != 16 * h * w:
+        raise ValueError("basis must hold 8*2*h*w values")
+    out = _BasisHomography.apply(basis, int(h), int(w), *weights)
+    return out[0] if len(out) == 1 else out
 
 
 # ----------------------------------------------------------------------------------------------

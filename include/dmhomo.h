@@ -187,6 +187,14 @@ DMH_API int dmh_basis_corner_offsets(const float* basis, const float* weight, fl
 DMH_API int dmh_basis_corner_offsets_backward(const float* basis, const float* grad_offsets,
                                       float* grad_weight, int B, int h, int w, void* stream);
 
+/* Fused cfg-2 prologue: for each of `n_sets` (<= 4) weight sets, weights[s] (B,8) -> basis flow at the 4
+ * image corners -> 4-point DLT -> H[s] (B,3,3); one launch, one warp per sample.  Replaces
+ * net.py:808-815 sampled at the corners + utils.py:55-101.  Backward writes grad_weight[s] (B,8). */
+DMH_API int dmh_basis_homography_forward(const float* basis, const float* const* weights, float* const* H, int n_sets,
+                                 int B, int h, int w, void* stream);
+DMH_API int dmh_basis_homography_backward(const float* basis, const float* const* H, const float* const* grad_H,
+                                  float* const* grad_weight, int n_sets, int B, int h, int w, void* stream);
+
 /* --- masks (A10, A11) -------------------------------------------------------------------- */
 /* get_gt_correspondence_mask / create_border_mask.  flow (B,2,h,w); either output may be null. */
 DMH_API int dmh_border_mask(const float* flow, uint8_t* mask_u8, float* mask_f32, int B, int h, int w,

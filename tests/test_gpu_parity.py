@@ -468,6 +468,35 @@ def test_cfg2_pipeline(variant):
         assert (tg.grad.cpu() - tc.grad).abs().max().item() < ATOL + 2e-2 * tc.grad.abs().max().item()
 
 
+def test_basis_homography_fused_matches_unfused():
+    """The one-launch cfg-2 prologue (weights -> corner offsets -> DLT, both directions) against the two-step ops
+    and the oracle, forward and backward."""
+    B, h, w = 5, 64, 96
+    basis = hem_utils.gen_basis(h, w)
+    gen = g(233)
+    wf, wb = synth.basis_weights(B, gen, 2.0), synth.basis_weights(B, gen, 2.0)
+    bd = basis.to(DEV)
+    src = port.corner_points(B, h, w)
+    gH = torch.randn(2, B, 3, 3, generator=gen)
+    # oracle
+    wfc, wbc = wf.clone().requires_grad_(True), wb.clone().requires_grad_(True)
+    Hf_o = port.dlt4(src, src + port.basis_corner_offsets(basis.reshape(1, 8, -1), wfc, h, w))
+    Hb_o = port.dlt4(src, src + port.basis_corner_offsets(basis.reshape(1, 8, -1), wbc, h, w))
+    ((Hf_o * gH[0]).sum() + (Hb_o * gH[1]).sum()).backward()
+    # fused
+    wfg, wbg = wf.to(DEV).requires_grad_(True), wb.to(DEV).requires_grad_(True)
+    Hf, Hb = ops.basis_homography(bd, h, w, wfg, wbg)
+    assert rel_fro(Hf.detach().cpu(), Hf_o.detach()) < 1e-5 and rel_fro(Hb.detach().cpu(), Hb_o.detach()) < 1e-5
+    ((Hf * gH[0].to(DEV)).sum() + (Hb * gH[1].to(DEV)).sum()).backward()
+    # unfused CUDA path: bit-identical forward (same arithmetic, one launch instead of three)
+    sd = src.to(DEV)
+    Hf2 = ops.dlt4(sd, sd + ops.basis_corner_offsets(bd, wf.to(DEV), h, w))
+    assert torch.equal(Hf.detach(), Hf2)
+    for tg, tc in ((wfg, wfc), (wbg, wbc)):
+        scale = max(1.0, tc.grad.abs().max().item())
+        assert (tg.grad.cpu() - tc.grad).abs().max().item() < 1e-3 * scale
+
+
 # ---------------------------------------------------------------------------------- DGM rendering
 def test_flow_to_rgb():
     flow = (np.random.default_rng(50).normal(size=(2, 24, 32, 2)) * 20).astype(np.float32)
