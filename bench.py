@@ -234,18 +234,36 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     import torch.distributed as tdist
 
+    # DMH_FORCE_DIST=1: exercise the multi-rank step (loss all-reduce inside the graph) on a single rank
+    dist_step = world > 1
+    if os.environ.get("DMH_FORCE_DIST") and world == 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        tdist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        dist_step = True
+
     wl = WORKLOADS[args.workload]
     st = PairStep(args.workload, dev, rank)
     K, W = args.steps, max(args.warmup, 3)
     stream = torch.cuda.Stream(dev)
 
+    red_base = torch.tensor([0.0, float(st.B)], device=dev)
+    red_scale = torch.tensor([float(st.B), 0.0], device=dev)
+    red_vec = torch.zeros(2, device=dev)
+
+    def reduce_loss(loss):
+        """The path's only exchange: one all-reduce(sum) of {loss * count, count} on the compute stream
+        (SURVEY.md section 8e); the global mean is red_vec[0] / red_vec[1].  One tiny kernel + one NCCL call.
+        Issued eagerly after the graph replay: NCCL collectives captured inside a CUDA graph hang on this
+        stack (tools/dist_probe.py --graph, NCCL 2.28.9 / torch 2.11) with more than one rank."""
+        torch.addcmul(red_base, red_scale, loss.detach().expand(2), out=red_vec)
+        tdist.all_reduce(red_vec)
+
     def step_eager(k, ev=None):
         st.zero_grads()
         loss = st.forward_backward(k, ev)
-        if world > 1:
-            st.loss_vec[0] = loss.detach().double() * st.B
-            st.loss_vec[1] = float(st.B)
-            tdist.all_reduce(st.loss_vec)
+        if dist_step:
+            reduce_loss(loss)
         return loss
 
     graphs, g_loss, g_events, launches_per_step = [], [], [], None
@@ -269,17 +287,15 @@ def run_ours(args):
                            torch.cuda.Event(enable_timing=True, external=True))
                     with torch.cuda.graph(g, pool=pool, stream=stream):
                         loss = st.forward_backward(k, evs)
-                        if world > 1:
-                            st.loss_vec[0] = loss.detach().double() * st.B
-                            st.loss_vec[1] = float(st.B)
-                            tdist.all_reduce(st.loss_vec)
                     pool = g.pool()
                     graphs.append(g)
                     g_loss.append(loss)
                     g_events.append(evs)
             except Exception as e:  # capture unsupported here: fall back to eager launches (still our kernels)
                 if rank == 0:
+                    import traceback
                     print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+                    traceback.print_exc()
                 graphs, g_loss, g_events, use_graph = [], [], [], False
                 torch.cuda.synchronize()
 
@@ -287,6 +303,8 @@ def run_ours(args):
             k = i % N_SETS
             if use_graph:
                 graphs[k].replay()
+                if dist_step:
+                    reduce_loss(g_loss[k])
                 return g_loss[k]
             return step_eager(k, timed_events)
 
@@ -294,13 +312,14 @@ def run_ours(args):
         for i in range(W):
             run_step(i)
         stream.synchronize()
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
+        # barrier + synchronize immediately before the timed region: every rank starts together
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kern_ms, eager_evs = [], []
         t_wall0 = time.time()
