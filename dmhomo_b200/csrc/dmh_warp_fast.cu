@@ -35,6 +35,7 @@ enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
 constexpr int kTuneDense = 0 | 3 << 4 | 4 << 8;
 constexpr int kTuneGeneral = 0 | 3 << 4 | 2 << 8;
 constexpr int kTuneDenseC3 = 0 | 3 << 4 | 3 << 8;   // cfg4 sweep: 80 registers, 3 CTAs/SM
+constexpr int kTileDefault = 1;    // 1 = dense S1 homography forward / fused launches go to dmh_warp_tile.cu
 constexpr int kStageDefault = 0;   // 0 off, 3 / 4 = staged kernel with a 3 / 4 CTAs-per-SM register budget
 
 // Explicit global-space accesses (the pinned bases below are opaque to the compiler, which would
@@ -526,6 +527,15 @@ int launch(const FastArgs& a, int n, long long tiles, int flags, cudaStream_t st
           return launched("warp_fast_kernel(staged)");
         }
       }
+      if constexpr (PARAM == DMH_PARAM_HOMOGRAPHY && PASS != PASS_BWD) {
+        // persistent tiled kernel (dmh_warp_tile.cu): bulk-copy staged window / target, packed fp32
+        static const int tile_mode = getenv("DMH_TILE") ? atoi(getenv("DMH_TILE")) : kTileDefault;
+        if ((flags & 4) && tile_mode > 0) {
+          FastArgs at = a;
+          const int rc = warp_tile_launch(at, n, PASS, CT, stream);
+          if (rc != 1) return rc;
+        }
+      }
       if constexpr (PASS != PASS_BWD) {
         // Measured (profiles/r1_tune_sweeps.txt): the paired kernel executes 21 % fewer instructions but its
         // register footprint halves the resident warps and it ends up ~3 % slower; opt-in until it is staged.
@@ -620,6 +630,10 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
   for (int i = 0; i < n; ++i)
     stage_ok = stage_ok && ((reinterpret_cast<uintptr_t>(d[i].src) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(d[i].target) & 15) == 0);
+  bool tile_ok = stage_ok && (d0.h % 2 == 0);
+  for (int i = 0; i < n; ++i)
+    tile_ok = tile_ok && ((reinterpret_cast<uintptr_t>(d[i].out) & 15) == 0) &&
+              ((reinterpret_cast<uintptr_t>(d[i].grad_target) & 15) == 0);
   if (n == 1) a.t[1] = a.t[0];
   a.B = d0.B; a.Hs = d0.Hs; a.Ws = d0.Ws; a.h = d0.h; a.w = d0.w;
   a.sx = d0.start_x; a.sy = d0.start_y;
@@ -629,11 +643,11 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
   if (tiles > 2147483647LL) return 1;
   if (d0.sampler == DMH_S1) {
     if (d0.param_kind == DMH_PARAM_HOMOGRAPHY)
-      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0), stream);
-    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0), stream);
+      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
+    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
   }
   if (d0.param_kind == DMH_PARAM_FLOW)
-    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0), stream);
+    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
   return 1;
 }
 

@@ -35,6 +35,8 @@ struct FastArgs {
   float sx, sy;
   // opaque identities for the packed (f32x2) kernels, see dmh_warp_pair.cu
   float one, neg_zero, minus_one;
+  // tiled persistent kernel (dmh_warp_tile.cu): length of the tile list, "start offsets are benign" flag
+  int n_tiles, start_sane;
 };
 
 // pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it
@@ -43,5 +45,9 @@ int warp_fast_try(const dmh_warp_desc* descs, int n, int pass, cudaStream_t stre
 
 // Paired (two rows per thread, packed fp32) form of the dense S1 forward / fused launches.
 int warp_pair_launch(FastArgs& a, int n, long long tiles, int param_kind, int pass, int C, cudaStream_t stream);
+
+// Persistent, shared-memory staged, packed form of the dense S1 homography launches (forward and fused).
+// Returns 1 when the shape is outside what it takes.
+int warp_tile_launch(FastArgs& a, int n, int pass, int C, cudaStream_t stream);
 
 }  // namespace dmh
