@@ -530,7 +530,8 @@ int launch(const FastArgs& a, int n, long long tiles, int flags, cudaStream_t st
       if constexpr (PARAM == DMH_PARAM_HOMOGRAPHY && PASS != PASS_BWD) {
         // persistent tiled kernel (dmh_warp_tile.cu): bulk-copy staged window / target, packed fp32
         static const int tile_mode = getenv("DMH_TILE") ? atoi(getenv("DMH_TILE")) : kTileDefault;
-        if ((flags & 4) && tile_mode > 0) {
+        // C = 3 stays on the scalar kernel (measured: cfg4 4.97 ms scalar vs 5.54 ms tiled); DMH_TILE=2 forces it
+        if ((flags & 4) && tile_mode > 0 && (CT == 1 || tile_mode > 1)) {
           FastArgs at = a;
           const int rc = warp_tile_launch(at, n, PASS, CT, stream);
           if (rc != 1) return rc;
