@@ -1,0 +1,170 @@
+"""GPU parity of the persistent tiled kernel (dmhomo_b200/csrc/dmh_warp_tile.cu) against the CPU oracle.
+
+The dense S1 homography launches (forward: warped image + validity mask; fused: masked L1 + all gradients)
+of C = 1 images go through the tiled kernel by default.  These cases aim at its own machinery: partial tile
+rows / columns, fewer tiles than CTAs, the dynamic tail of the tile schedule, windows that do not cover the
+tile (global fallback taps), homographies outside the packed division's proven domain (scalar __fdiv_rn
+path), start offsets, and - in a subprocess with DMH_TILE=2 - the C = 3 instantiation.
+Bars: warped pixels and masks bit-exact, loss / gradients within 1e-4 absolute (north_star).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from dmhomo_b200 import ops, synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ATOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _homographies(B, h, w, rho, seed):
+    src = port.corner_points(B, h, w)
+    return port.dlt4(src, src + synth.corner_offsets(B, rho, g(seed)))
+
+
+def _check_forward(img, H, start=0):
+    B, C, h, w = img.shape
+    flow, _ = port.homography_to_flow(H, h, w, start=start)
+    ref = port.get_warp_flow(img, flow, start=start)
+    out, mask = ops.warp(img.to(DEV), H.to(DEV), kind=ops.PARAM_HOMOGRAPHY, return_mask=True, start=start)
+    assert torch.equal(mask.cpu(), port.correspondence_mask(flow)), "validity mask differs"
+    assert torch.equal(out.cpu(), ref), f"warped pixels differ (max {(out.cpu() - ref).abs().max().item():.3e})"
+
+
+@pytest.mark.parametrize(
+    "B,h,w,rho,start",
+    [
+        (3, 360, 640, 32.0, 0),     # cfg1 shape: last tile row is partial (360 = 5 * 64 + 40)
+        (2, 320, 576, 32.0, 0),     # cfg2 shape
+        (2, 128, 100, 8.0, 0),      # partial tile column (w % 64 != 0), w % 4 == 0
+        (1, 64, 64, 4.0, 0),        # one tile: far fewer tiles than CTAs, everything in the static chunk of CTA 0
+        (5, 192, 320, 24.0, 3),     # start offset (get_grid start = 3)
+        (2, 256, 256, 16.0, 0.5),   # fractional start
+        (150, 64, 128, 6.0, 0),     # 300 tiles on 148 CTAs: static chunks of 1-2 tiles + dynamic tail
+    ],
+)
+def test_tile_forward_bit_exact(B, h, w, rho, start):
+    img = synth.noise_images(B, 1, h, w, g(101))
+    _check_forward(img, _homographies(B, h, w, rho, 102), start)
+
+
+def test_tile_forward_strong_warp_uses_global_taps():
+    """Corner offsets of 40 % of the image: the pre-image of a 64 x 64 tile does not fit the staged window,
+    so part of the taps come from global memory - the result must not depend on the window."""
+    B, h, w = 3, 256, 256
+    img = synth.noise_images(B, 1, h, w, g(111))
+    _check_forward(img, _homographies(B, h, w, 100.0, 112))
+
+
+def test_tile_forward_scaled_homography_takes_scalar_division():
+    """H * 2^30 is the same projective map but lies outside the magnitude range for which the packed Newton
+    division is proven exact: the tile must fall back to scalar IEEE division and stay bit-exact."""
+    B, h, w = 2, 128, 192
+    img = synth.noise_images(B, 1, h, w, g(121))
+    H = _homographies(B, h, w, 12.0, 122) * float(2 ** 30)
+    _check_forward(img, H)
+    _check_forward(img, _homographies(B, h, w, 12.0, 122) * float(2.0 ** -30))
+
+
+def test_tile_forward_horizon_inside_image():
+    """A homography whose T changes sign inside the image (and hits the |T| < 1e-7 epsilon rule region):
+    no window is staged for such tiles; coordinates, masks and pixels still follow the reference bit for bit."""
+    B, h, w = 2, 128, 128
+    img = synth.noise_images(B, 1, h, w, g(131))
+    H = _homographies(B, h, w, 4.0, 132)
+    H[:, 2, 0] = -1.0 / 70.0   # T = 1 - x / 70 + ...: zero near x = 70
+    _check_forward(img, H)
+
+
+def test_tile_identity_zeroes_last_row_and_col():
+    B, h, w = 2, 64, 128
+    img = synth.noise_images(B, 1, h, w, g(141))
+    H = torch.eye(3).repeat(B, 1, 1)
+    out, mask = ops.warp(img.to(DEV), H.to(DEV), kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
+    ref = img.clone()
+    ref[:, :, -1, :] = 0
+    ref[:, :, :, -1] = 0
+    assert torch.equal(out.cpu(), ref)
+    assert bool(mask.all())
+
+
+@pytest.mark.parametrize("B,h,w,rho", [(3, 320, 576, 32.0), (2, 360, 640, 32.0), (160, 64, 64, 5.0), (2, 256, 256, 90.0)])
+def test_tile_fused_loss_and_gradients(B, h, w, rho):
+    img1, img2 = synth.noise_images(B, 1, h, w, g(151)), synth.noise_images(B, 1, h, w, g(152))
+    Hf, Hb = _homographies(B, h, w, rho, 153), _homographies(B, h, w, rho, 154)
+    i1c, i2c = img1.clone().requires_grad_(True), img2.clone().requires_grad_(True)
+    Hfc, Hbc = Hf.clone().requires_grad_(True), Hb.clone().requires_grad_(True)
+    ff, fb = port.homography_to_flow(Hfc, h, w)[0], port.homography_to_flow(Hbc, h, w)[0]
+    mf, mb = port.border_mask(ff).unsqueeze(1), port.border_mask(fb).unsqueeze(1)
+    ref = port.masked_l1(mf, i1c, port.get_warp_flow(i2c, ff)) + port.masked_l1(mb, i2c, port.get_warp_flow(i1c, fb))
+    ref.backward()
+    i1g, i2g = img1.to(DEV).requires_grad_(True), img2.to(DEV).requires_grad_(True)
+    Hfg, Hbg = Hf.to(DEV).requires_grad_(True), Hb.to(DEV).requires_grad_(True)
+    loss = ops.warp_loss([ops.WarpTerm(i2g, i1g, Hfg), ops.WarpTerm(i1g, i2g, Hbg)], kind=ops.PARAM_HOMOGRAPHY)
+    assert abs(loss.item() - ref.item()) < 1e-5
+    loss.backward()
+    assert (i1g.grad.cpu() - i1c.grad).abs().max().item() < ATOL
+    assert (i2g.grad.cpu() - i2c.grad).abs().max().item() < ATOL
+    for a, b in ((Hfg.grad.cpu(), Hfc.grad), (Hbg.grad.cpu(), Hbc.grad)):
+        assert ((a - b).norm() / b.norm()).item() < 1e-3
+
+
+def test_tile_fused_repeatable_and_counter_slots():
+    """More launches than counter slots (64): the self-resetting tile counters must leave every launch with the
+    full tile list (identical loss every time)."""
+    B, h, w = 4, 128, 192
+    img1, img2 = synth.noise_images(B, 1, h, w, g(161)).to(DEV), synth.noise_images(B, 1, h, w, g(162)).to(DEV)
+    Hf, Hb = _homographies(B, h, w, 10.0, 163).to(DEV), _homographies(B, h, w, 10.0, 164).to(DEV)
+    first = None
+    for _ in range(150):
+        loss = ops.warp_loss([ops.WarpTerm(img2, img1, Hf), ops.WarpTerm(img1, img2, Hb)], kind=ops.PARAM_HOMOGRAPHY)
+        v = loss.item()
+        first = v if first is None else first
+        assert abs(v - first) < 1e-6
+
+
+_C3_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from dmhomo_b200 import ops, synth
+from oracle import port
+g = lambda s: torch.Generator().manual_seed(s)
+B, C, h, w = 2, 3, 128, 192
+img1, img2 = synth.noise_images(B, C, h, w, g(171)), synth.noise_images(B, C, h, w, g(172))
+src = port.corner_points(B, h, w)
+Hf = port.dlt4(src, src + synth.corner_offsets(B, 12.0, g(173)))
+Hb = port.dlt4(src, src + synth.corner_offsets(B, 12.0, g(174)))
+flow, _ = port.homography_to_flow(Hf, h, w)
+out, mask = ops.warp(img2.cuda(), Hf.cuda(), kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
+assert torch.equal(out.cpu(), port.get_warp_flow(img2, flow)), "C=3 tiled forward differs"
+assert torch.equal(mask.cpu(), port.correspondence_mask(flow))
+i1c, i2c = img1.clone().requires_grad_(True), img2.clone().requires_grad_(True)
+ff, fb = port.homography_to_flow(Hf, h, w)[0], port.homography_to_flow(Hb, h, w)[0]
+mf, mb = port.border_mask(ff).unsqueeze(1), port.border_mask(fb).unsqueeze(1)
+ref = port.masked_l1(mf, i1c, port.get_warp_flow(i2c, ff)) + port.masked_l1(mb, i2c, port.get_warp_flow(i1c, fb))
+ref.backward()
+i1g, i2g = img1.cuda().requires_grad_(True), img2.cuda().requires_grad_(True)
+loss = ops.warp_loss([ops.WarpTerm(i2g, i1g, Hf.cuda().requires_grad_(True)), ops.WarpTerm(i1g, i2g, Hb.cuda().requires_grad_(True))],
+                     kind=ops.PARAM_HOMOGRAPHY)
+loss.backward()
+assert abs(loss.item() - ref.item()) < 1e-5
+assert (i1g.grad.cpu() - i1c.grad).abs().max().item() < 1e-4
+assert (i2g.grad.cpu() - i2c.grad).abs().max().item() < 1e-4
+print("C3 OK")
+"""
+
+
+def test_tile_c3_instantiation_in_subprocess():
+    env = dict(os.environ, DMH_TILE="2")
+    r = subprocess.run([sys.executable, "-c", _C3_SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "C3 OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
