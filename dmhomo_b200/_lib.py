@@ -70,6 +70,7 @@ SIGNATURES = {
     "dmh_version": [],
     "dmh_last_error_string": [],
     "dmh_launch_count": [],
+    "dmh_last_kernel_name": [],
     "dmh_warp_forward": [C.POINTER(WarpDesc), _i, _fp],
     "dmh_warp_backward": [C.POINTER(WarpDesc), _i, _fp],
     "dmh_loss_finish": [C.POINTER(_fp), C.POINTER(_fp), _i, _i, _f, _fp, _fp],
@@ -94,7 +95,7 @@ SIGNATURES = {
     "dmh_eval_point_error": [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_to_homography_ls": [_fp, _fp, _fp, _i, _i, _i, _fp],
 }
-_RESTYPES = {"dmh_last_error_string": C.c_char_p, "dmh_launch_count": C.c_uint64}
+_RESTYPES = {"dmh_last_error_string": C.c_char_p, "dmh_last_kernel_name": C.c_char_p, "dmh_launch_count": C.c_uint64}
 
 _lib = None
 _lock = threading.Lock()
@@ -136,3 +137,8 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib().dmh_launch_count())
+
+
+def last_kernel_name():
+    n = lib().dmh_last_kernel_name()
+    return n.decode() if n else ""

@@ -15,6 +15,7 @@ namespace dmh {
 // ---- host side -----------------------------------------------------------------------
 extern thread_local char g_last_error[512];
 extern std::atomic<uint64_t> g_launches;
+extern thread_local const char* g_last_kernel;
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -27,6 +28,7 @@ inline int fail(int code, const char* fmt, ...) {
 // Call right after a <<<>>> launch: counts it and turns launch errors into DMH_ECUDA.
 inline int launched(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_kernel = what;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(DMH_ECUDA, "%s: %s", what, cudaGetErrorString(e));
   return DMH_OK;

@@ -90,11 +90,22 @@ def _desc(sampler, kind, src, param, h, w, **kw):
     return d
 
 
+warp_timing_events = None   # optional (begin, end) torch.cuda.Event pair recorded tightly around the next warp launches
+last_warp_kernel = ""   # diagnostic: the kernel the last warp launch of this process went to (bench.py's roofline label)
+
+
 def _run_warp(descs, dev, backward=False):
     arr = (L.WarpDesc * len(descs))(*descs)
     fn = L.lib().dmh_warp_backward if backward else L.lib().dmh_warp_forward
+    ev = warp_timing_events
     with torch.cuda.device(dev):
+        if ev is not None:
+            ev[0].record()
         L.check(fn(arr, len(descs), _stream(dev)), "warp_backward" if backward else "warp_forward")
+        if ev is not None:
+            ev[1].record()
+    global last_warp_kernel
+    last_warp_kernel = L.last_kernel_name()
 
 
 def _param_shape_check(kind, param, B, h, w, divide):

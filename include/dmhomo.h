@@ -132,6 +132,9 @@ DMH_API int dmh_version(void);
 DMH_API const char* dmh_last_error_string(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 DMH_API uint64_t dmh_launch_count(void);
+/* Name of the kernel the calling thread launched last through this library ("" before the first launch);
+ * bench.py labels its roofline object with it. */
+DMH_API const char* dmh_last_kernel_name(void);
 
 /* --- warp (A6-A9, A12-A14) -------------------------------------------------------------
  * dmh_warp_forward: get_warp_flow / transformer / WarpImages / warp / warp_with_mapping /

@@ -86,6 +86,83 @@ def test_tile_forward_horizon_inside_image():
     _check_forward(img, H)
 
 
+def _affine(B, sx, sy, tx, ty, shear=0.0):
+    H = torch.eye(3).repeat(B, 1, 1)
+    H[:, 0, 0], H[:, 1, 1], H[:, 0, 1], H[:, 0, 2], H[:, 1, 2] = sx, sy, shear, tx, ty
+    return H
+
+
+@pytest.mark.parametrize("tx,ty", [(2.0, 2.0), (1.99, 2.01), (2.5, 1.0), (0.0, 0.0), (-3.0, 7.25), (61.0, 3.0), (62.0, 62.0),
+                                   (63.5, 0.5), (130.0, -70.0)])
+def test_tile_interior_flag_boundaries_translation(tx, ty):
+    """Pure translations put the pre-image of every tile at a known distance from the source border: offsets
+    around the 2-pixel margin of the interior-tile proof (clamp-free, mask-free body) flip tiles between the two
+    bodies; both must reproduce the reference bit for bit, including the zeroed / clamped border taps."""
+    B, h, w = 2, 192, 256
+    img = synth.noise_images(B, 1, h, w, g(181))
+    _check_forward(img, _affine(B, 1.0, 1.0, tx, ty))
+
+
+@pytest.mark.parametrize("sx,sy,shear", [(1.07, 0.93, 0.0), (0.9, 1.1, 0.05), (1.0, 1.25, -0.1), (0.5, 0.5, 0.0)])
+def test_tile_interior_scaled_rows_skip_and_repeat(sx, sy, shear):
+    """Vertical scale != 1: tap rows are skipped (sy > 1) or repeated (sy < 1) between consecutive output rows, so
+    the vertical merging of the scatter takes its rare-seam branch in interior tiles; forward bit-exact, loss and
+    gradients within 1e-4."""
+    B, h, w = 2, 256, 320
+    img1, img2 = synth.noise_images(B, 1, h, w, g(191)), synth.noise_images(B, 1, h, w, g(192))
+    H = _affine(B, sx, sy, 20.0 * (1 - sx) + 3.3, 30.0 * (1 - sy) + 4.7, shear)
+    _check_forward(img2, H)
+    i1c, i2c, Hc = img1.clone().requires_grad_(True), img2.clone().requires_grad_(True), H.clone().requires_grad_(True)
+    ff = port.homography_to_flow(Hc, h, w)[0]
+    ref = port.masked_l1(port.border_mask(ff).unsqueeze(1), i1c, port.get_warp_flow(i2c, ff))
+    ref.backward()
+    i1g, i2g = img1.to(DEV).requires_grad_(True), img2.to(DEV).requires_grad_(True)
+    Hg = H.to(DEV).requires_grad_(True)
+    loss = ops.warp_loss([ops.WarpTerm(i2g, i1g, Hg)], kind=ops.PARAM_HOMOGRAPHY)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert (i1g.grad.cpu() - i1c.grad).abs().max().item() < ATOL
+    assert (i2g.grad.cpu() - i2c.grad).abs().max().item() < ATOL
+    assert ((Hg.grad.cpu() - Hc.grad).norm() / Hc.grad.norm()).item() < 1e-3
+
+
+_AB_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from dmhomo_b200 import ops, synth
+from oracle import port
+g = lambda s: torch.Generator().manual_seed(s)
+B, h, w = 6, 320, 576
+img1, img2 = synth.noise_images(B, 1, h, w, g(201)).cuda(), synth.noise_images(B, 1, h, w, g(202)).cuda()
+src = port.corner_points(B, h, w)
+Hf = port.dlt4(src, src + synth.corner_offsets(B, 32.0, g(203))).cuda()
+out, mask = ops.warp(img2, Hf, kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
+i1, i2, Hg = img1.clone().requires_grad_(True), img2.clone().requires_grad_(True), Hf.clone().requires_grad_(True)
+loss = ops.warp_loss([ops.WarpTerm(i2, i1, Hg)], kind=ops.PARAM_HOMOGRAPHY)
+loss.backward()
+torch.save(dict(out=out.cpu(), mask=mask.cpu(), loss=loss.detach().cpu(), g1=i1.grad.cpu(), g2=i2.grad.cpu(), gH=Hg.grad.cpu()), sys.argv[1])
+"""
+
+
+def test_tile_interior_body_matches_general_body(tmp_path):
+    """A/B in subprocesses: DMH_TILE_INTERIOR=0 forces every tile through the general (clamping, masking) body.
+    Forward output, mask and dL/dtarget (no atomics involved) must be bit-identical; the scattered dL/dsrc and the
+    reductions only differ by fp32 summation order."""
+    res = []
+    for flag in ("1", "0"):
+        path = str(tmp_path / f"ab{flag}.pt")
+        env = dict(os.environ, DMH_TILE_INTERIOR=flag)
+        r = subprocess.run([sys.executable, "-c", _AB_SCRIPT % ROOT, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        res.append(torch.load(path))
+    a, b = res
+    assert torch.equal(a["out"], b["out"]) and torch.equal(a["mask"], b["mask"])
+    assert torch.equal(a["g1"], b["g1"]), "dL/dtarget differs between the interior and the general body"
+    assert (a["g2"] - b["g2"]).abs().max().item() < 1e-7
+    assert abs(a["loss"].item() - b["loss"].item()) < 1e-6
+    assert ((a["gH"] - b["gH"]).norm() / b["gH"].norm()).item() < 1e-4
+
+
 def test_tile_identity_zeroes_last_row_and_col():
     B, h, w = 2, 64, 128
     img = synth.noise_images(B, 1, h, w, g(141))
