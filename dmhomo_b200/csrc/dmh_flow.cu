@@ -482,7 +482,10 @@ extern "C" int dmh_loss_finish(const double* const* acc, const float* const* sam
 extern "C" int dmh_scale_inplace(float* x, int64_t n, const float* g, void* stream) {
   DMH_REQUIRE(x && g, "scale_inplace: null pointer");
   DMH_REQUIRE(n > 0, "scale_inplace: n must be positive");
-  scale_inplace_kernel<<<blocks_for(n), kThreads, 0, as_stream(stream)>>>(x, n, g);
+  // grid-stride over a bounded grid: with a unit upstream gradient (the usual case) every block returns at once,
+  // and a grid of n / threads blocks would spend microseconds just being scheduled
+  const long long nb = blocks_for(n);
+  scale_inplace_kernel<<<(unsigned)(nb < 8 * kNumSMs ? nb : 8 * kNumSMs), kThreads, 0, as_stream(stream)>>>(x, n, g);
   return launched("scale_inplace_kernel");
 }
 

@@ -38,7 +38,7 @@ struct FastArgs {
   // tiled persistent kernel (dmh_warp_tile.cu): length of the tile list, "start offsets are benign" flag
   int n_tiles, start_sane;
   int n_static, counter_slot;   // guided schedule: statically chunked prefix of the tile list, counter slot
-  int interior_ok;              // 0: never take the interior-tile body (DMH_TILE_INTERIOR=0, A/B checks)
+  int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body; DMH_TILE_INTERIOR=0 for A/B checks
 };
 
 // pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it

@@ -145,22 +145,24 @@ torch.save(dict(out=out.cpu(), mask=mask.cpu(), loss=loss.detach().cpu(), g1=i1.
 
 
 def test_tile_interior_body_matches_general_body(tmp_path):
-    """A/B in subprocesses: DMH_TILE_INTERIOR=0 forces every tile through the general (clamping, masking) body.
+    """A/B in subprocesses: DMH_TILE_INTERIOR=0 forces every tile through the general (clamping, masking) body,
+    1 allows whole interior tiles only, 3 (default) adds the per-row-pair vote inside border tiles.
     Forward output, mask and dL/dtarget (no atomics involved) must be bit-identical; the scattered dL/dsrc and the
     reductions only differ by fp32 summation order."""
     res = []
-    for flag in ("1", "0"):
+    for flag in ("3", "1", "0"):   # interior + mixed (default) / interior only / general body only
         path = str(tmp_path / f"ab{flag}.pt")
         env = dict(os.environ, DMH_TILE_INTERIOR=flag)
         r = subprocess.run([sys.executable, "-c", _AB_SCRIPT % ROOT, path], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         res.append(torch.load(path))
-    a, b = res
-    assert torch.equal(a["out"], b["out"]) and torch.equal(a["mask"], b["mask"])
-    assert torch.equal(a["g1"], b["g1"]), "dL/dtarget differs between the interior and the general body"
-    assert (a["g2"] - b["g2"]).abs().max().item() < 1e-7
-    assert abs(a["loss"].item() - b["loss"].item()) < 1e-6
-    assert ((a["gH"] - b["gH"]).norm() / b["gH"].norm()).item() < 1e-4
+    b = res[-1]
+    for a in res[:-1]:
+        assert torch.equal(a["out"], b["out"]) and torch.equal(a["mask"], b["mask"])
+        assert torch.equal(a["g1"], b["g1"]), "dL/dtarget differs between the fast and the general body"
+        assert (a["g2"] - b["g2"]).abs().max().item() < 1e-7
+        assert abs(a["loss"].item() - b["loss"].item()) < 1e-6
+        assert ((a["gH"] - b["gH"]).norm() / b["gH"].norm()).item() < 1e-4
 
 
 def test_tile_identity_zeroes_last_row_and_col():
