@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmhomo.so")
+# DMH_LIB: development knob, an alternative build of the same library (tools/build_variants.sh A/B runs)
+LIB_PATH = os.environ.get("DMH_LIB") or os.path.join(_HERE, "libdmhomo.so")
 ABI_VERSION = 1
 
 # enums of include/dmhomo.h
