@@ -11,44 +11,52 @@
 
 namespace dmh {
 
-// Solves M z = rhs for the 8x8 system whose row `lane` (lane < 8) is m[0..7] | m[8].
-// Returns z_k broadcast in sol[k] on every lane.
+// Solves M z = rhs for the 8x8 system whose row r = lane & 7 is m[0..7] | m[8] (the four 8-lane groups of the warp
+// hold identical copies and run in lockstep).  Returns z_k broadcast in sol[k] on every lane.
+// Gauss-Jordan with partial pivoting among the rows not yet used as a pivot: every other row is eliminated at each
+// step, so there is no serial back-substitution - the latency chain is 8 x (3 shuffle rounds + one fp64 division +
+// one FMA) and a final division, which is what this launch costs (it is latency-bound: 128 systems, 9 KB of data).
 __device__ __forceinline__ void solve8_warp(double (&m)[9], int lane, double (&sol)[8]) {
+  const int r = lane & 7;
   bool used = false;
+  int mycol = 0;
   int piv[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    // pivot search: largest |m[k]| among unused rows, lowest lane wins ties
-    double best = (lane < 8 && !used) ? fabs(m[k]) : -1.0;
-    int who = lane;
+    // pivot search: largest |m[k]| among unused rows, lowest row wins ties
+    double best = used ? -1.0 : fabs(m[k]);
+    int who = r;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+    for (int o = 4; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o, 8);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, o, 8);
       if (ob > best || (ob == best && ow < who)) {
         best = ob;
         who = ow;
       }
     }
     piv[k] = who;
-    const double pk = __shfl_sync(0xffffffffu, m[k], who);
-    const bool elim = (lane < 8) && !used && (lane != who);
-    const double f = elim ? m[k] / pk : 0.0;
+    const double pk = __shfl_sync(0xffffffffu, m[k], who, 8);
+    const bool is_piv = (r == who);
+    const double f = is_piv ? 0.0 : m[k] / pk;
 #pragma unroll
     for (int j = k + 1; j < 9; ++j) {
-      const double pj = __shfl_sync(0xffffffffu, m[j], who);
-      if (elim) m[j] = fma(-f, pj, m[j]);
+      const double pj = __shfl_sync(0xffffffffu, m[j], who, 8);
+      m[j] = fma(-f, pj, m[j]);
     }
-    if (lane == who) used = true;
+    if (is_piv) {
+      used = true;
+      mycol = k;
+    }
   }
+  // row r pivoted column mycol: x_mycol = m[8] / m[mycol] (static register indexing)
+  double d = m[0];
 #pragma unroll
-  for (int k = 7; k >= 0; --k) {
-    double acc = m[8];
+  for (int q = 1; q < 8; ++q)
+    if (mycol == q) d = m[q];
+  const double xr = m[8] / d;
 #pragma unroll
-    for (int j = k + 1; j < 8; ++j) acc = fma(-m[j], sol[j], acc);
-    const double xk = acc / m[k];
-    sol[k] = __shfl_sync(0xffffffffu, xk, piv[k]);
-  }
+  for (int k = 0; k < 8; ++k) sol[k] = __shfl_sync(0xffffffffu, xr, piv[k], 8);
 }
 
 // Row `r` (0..7) of the DLT system for point i = r/2 (App. A.1).
@@ -66,6 +74,21 @@ __device__ __forceinline__ void dlt_row(int r, float x, float y, float u, float 
   m[8] = t;
 }
 
+// Element (row j, column c) of the same system with a run-time column (the adjoint solves need column r of A as
+// their row): selects instead of an indexed local array.
+__device__ __forceinline__ double dlt_elem(int j, int c, float x, float y, float u, float v) {
+  const bool top = (j & 1) == 0;
+  const float t = top ? u : v;
+  const int cc = top ? c : c - 3;
+  float val = 0.f;
+  if (cc == 0) val = x;
+  if (cc == 1) val = y;
+  if (cc == 2) val = 1.f;
+  if (c == 6) val = -mul_rn(t, x);
+  if (c == 7) val = -mul_rn(t, y);
+  return (double)val;
+}
+
 __global__ void __launch_bounds__(128) dlt4_fwd_kernel(const float* __restrict__ src, const float* __restrict__ dst,
                                                        float* __restrict__ H, int N) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -77,8 +100,11 @@ __global__ void __launch_bounds__(128) dlt4_fwd_kernel(const float* __restrict__
   double m[9], sol[8];
   dlt_row(r, x, y, u, v, m);
   solve8_warp(m, lane, sol);
-  if (lane < 8) H[(size_t)n * 9 + lane] = (float)sol[lane];
-  if (lane == 8) H[(size_t)n * 9 + 8] = 1.0f;
+  float hv = 1.0f;                       // lane 8 writes h22 = 1
+#pragma unroll
+  for (int q = 0; q < 8; ++q)            // static register indexing
+    if (lane == q) hv = (float)sol[q];
+  if (lane < 9) H[(size_t)n * 9 + lane] = hv;
 }
 
 // h = A^-1 b.  With z = A^-T g_h:
@@ -98,9 +124,7 @@ __global__ void __launch_bounds__(128) dlt4_bwd_kernel(const float* __restrict__
     const int i = j >> 1;
     const float x = __ldg(src + (size_t)n * 8 + 2 * i), y = __ldg(src + (size_t)n * 8 + 2 * i + 1);
     const float u = __ldg(dst + (size_t)n * 8 + 2 * i), v = __ldg(dst + (size_t)n * 8 + 2 * i + 1);
-    double row[9];
-    dlt_row(j, x, y, u, v, row);
-    m[j] = row[r];
+    m[j] = dlt_elem(j, r, x, y, u, v);
   }
   m[8] = (double)__ldg(gH + (size_t)n * 9 + r);
   double z[8];
@@ -178,7 +202,7 @@ __device__ __forceinline__ void corner_xy(int c, int h, int w, float& x, float& 
   y = (c >> 1) ? (float)(h - 1) : 0.f;
 }
 
-__global__ void __launch_bounds__(128) basis_h_fwd_kernel(const float* __restrict__ basis, BasisHArgs args, int n_sets,
+__global__ void __launch_bounds__(128) basis_h_fwd_kernel(const float* __restrict__ basis, const __grid_constant__ BasisHArgs args, int n_sets,
                                                           int B, int h, int w) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= n_sets * B) return;  // warp-uniform
@@ -188,8 +212,15 @@ __global__ void __launch_bounds__(128) basis_h_fwd_kernel(const float* __restric
   const int c = j >> 1, xy = j & 1;
   const int py = (c >> 1) ? h - 1 : 0, px = (c & 1) ? w - 1 : 0;
   const size_t plane = (size_t)h * w, po = (size_t)py * w + px;
-  float off = mul_rn(__ldg(basis + (size_t)xy * plane + po), __ldg(wp));
-  for (int k = 1; k < 8; ++k) off = add_rn(off, mul_rn(__ldg(basis + (size_t)(2 * k + xy) * plane + po), __ldg(wp + k)));
+  float bv[8], wv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {      // all 16 loads in flight at once
+    bv[k] = __ldg(basis + (size_t)(2 * k + xy) * plane + po);
+    wv[k] = __ldg(wp + k);
+  }
+  float off = mul_rn(bv[0], wv[0]);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) off = add_rn(off, mul_rn(bv[k], wv[k]));
   // row r = lane & 7 of the system needs (x, y, u, v) of point i = r / 2: u, v = corner + offset
   const int i = j >> 1;
   float x, y;
@@ -200,13 +231,16 @@ __global__ void __launch_bounds__(128) basis_h_fwd_kernel(const float* __restric
   dlt_row(j, x, y, u, v, m);
   solve8_warp(m, lane, sol);
   float* H = args.H[set] + (size_t)b * 9;
-  if (lane < 8) H[lane] = (float)sol[lane];
-  if (lane == 8) H[8] = 1.0f;
+  float hv = 1.0f;                       // lane 8 writes h22 = 1
+#pragma unroll
+  for (int q = 0; q < 8; ++q)            // static register indexing
+    if (lane == q) hv = (float)sol[q];
+  if (lane < 9) H[lane] = hv;
 }
 
 // grad_H -> grad_weight (written): adjoint DLT solve (as dlt4_bwd_kernel), then the transpose of the corner
 // sampling: g_w[k] = sum_{corner, xy} g_off[corner, xy] * basis[k, xy, corner].
-__global__ void __launch_bounds__(128) basis_h_bwd_kernel(const float* __restrict__ basis, BasisHArgs args, int n_sets,
+__global__ void __launch_bounds__(128) basis_h_bwd_kernel(const float* __restrict__ basis, const __grid_constant__ BasisHArgs args, int n_sets,
                                                           int B, int h, int w) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= n_sets * B) return;
@@ -228,9 +262,7 @@ __global__ void __launch_bounds__(128) basis_h_bwd_kernel(const float* __restric
   double m[9];
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
-    double row[9];
-    dlt_row(jj, xs[jj >> 1], ys[jj >> 1], us[jj >> 1], vs[jj >> 1], row);
-    m[jj] = row[r];
+    m[jj] = dlt_elem(jj, r, xs[jj >> 1], ys[jj >> 1], us[jj >> 1], vs[jj >> 1]);
   }
   m[8] = (double)__ldg(args.grad_H[set] + (size_t)b * 9 + r);
   double z[8];

@@ -38,6 +38,7 @@ struct FastArgs {
   // tiled persistent kernel (dmh_warp_tile.cu): length of the tile list, "start offsets are benign" flag
   int n_tiles, start_sane;
   int n_static, counter_slot;   // guided schedule: statically chunked prefix of the tile list, counter slot
+  int chunk;                    // tiles per dynamic claim
   int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body; DMH_TILE_INTERIOR=0 for A/B checks
 };
 
