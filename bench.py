@@ -248,21 +248,32 @@ def run_ours(args):
 
     red_base = torch.tensor([0.0, float(st.B)], device=dev)
     red_scale = torch.tensor([float(st.B), 0.0], device=dev)
-    red_vec = torch.zeros(2, device=dev)
+    red_vecs = [torch.zeros(2, device=dev) for _ in range(N_SETS)]
+    comm_stream = torch.cuda.Stream(dev)
+    step_done = [torch.cuda.Event() for _ in range(N_SETS)]
+    comm_done = [torch.cuda.Event() for _ in range(N_SETS)]
 
-    def reduce_loss(loss):
-        """The path's only exchange: one all-reduce(sum) of {loss * count, count} on the compute stream
-        (SURVEY.md section 8e); the global mean is red_vec[0] / red_vec[1].  One tiny kernel + one NCCL call.
-        Issued eagerly after the graph replay: NCCL collectives captured inside a CUDA graph hang on this
-        stack (tools/dist_probe.py --graph, NCCL 2.28.9 / torch 2.11) with more than one rank."""
-        torch.addcmul(red_base, red_scale, loss.detach().expand(2), out=red_vec)
-        tdist.all_reduce(red_vec)
+    def reduce_loss(loss, k):
+        """The path's only exchange: one all-reduce(sum) of {loss * count, count}; the global
+        mean is red_vecs[k][0] / red_vecs[k][1].  One tiny kernel + one NCCL call, on a second stream behind the step's
+        event so that the next step's kernels do not wait for the collective's latency (nothing downstream of the
+        step consumes the reduced scalar); the compute stream waits for it before the same input set is reused, and
+        the timed region ends with a full device synchronize.  Issued eagerly, never captured: NCCL collectives
+        inside a CUDA graph hang on this stack (tools/dist_probe.py --graph, NCCL 2.28.9 / torch 2.11) with > 1 rank."""
+        cur = torch.cuda.current_stream(dev)
+        step_done[k].record(cur)
+        comm_stream.wait_event(step_done[k])
+        loss.record_stream(comm_stream)
+        with torch.cuda.stream(comm_stream):
+            torch.addcmul(red_base, red_scale, loss.detach().expand(2), out=red_vecs[k])
+            tdist.all_reduce(red_vecs[k])
+            comm_done[k].record(comm_stream)
 
     def step_eager(k, ev=None):
         st.zero_grads()
         loss = st.forward_backward(k, ev)
         if dist_step:
-            reduce_loss(loss)
+            reduce_loss(loss, k)
         return loss
 
     graphs, g_loss, g_events, launches_per_step = [], [], [], None
@@ -301,9 +312,11 @@ def run_ours(args):
         def run_step(i, timed_events=None):
             k = i % N_SETS
             if use_graph:
+                if dist_step:
+                    stream.wait_event(comm_done[k])   # the previous collective on this set's loss scalar has read it
                 graphs[k].replay()
                 if dist_step:
-                    reduce_loss(g_loss[k])
+                    reduce_loss(g_loss[k], k)
                 return g_loss[k]
             return step_eager(k, timed_events)
 
@@ -331,6 +344,9 @@ def run_ours(args):
                 evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 run_step(i, evs)
                 eager_evs.append(evs)
+        if dist_step:
+            for ev in comm_done:          # the timed region ends when the last collective has finished, too
+                stream.wait_event(ev)
         e1.record(stream)
         stream.synchronize()
         if world > 1:
@@ -351,7 +367,7 @@ def run_ours(args):
             time.sleep(0.15)
             sampler.stop()
         clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
-        final_loss = float(run_step(0))
+        final_loss = float(run_step(0).detach())
 
         # ---- end-to-end: host buffers in, loss out, every step ---------------------------------------
         B, C, h, w = st.B, st.C, st.h, st.w
