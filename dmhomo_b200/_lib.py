@@ -95,6 +95,9 @@ SIGNATURES = {
     "dmh_warp_perspective": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_eval_point_error": [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_to_homography_ls": [_fp, _fp, _fp, _i, _i, _i, _fp],
+    "dmh_pairs_u8_to_gray": [_fp, _fp, _fp, _fp, _fp, C.POINTER(_d), C.POINTER(_d), _i, _i, _i, _i, _i, _fp],
+    "dmh_flow_upsample": [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
+    "dmh_flow_upsample_backward": [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
 }
 _RESTYPES = {"dmh_last_error_string": C.c_char_p, "dmh_last_kernel_name": C.c_char_p, "dmh_launch_count": C.c_uint64}
 

@@ -3,7 +3,7 @@
     from dmhomo_b200.compat import hem_utils            # HEM/model/utils.py
     from dmhomo_b200.compat import hem_net              # HEM/model/net.py (DLT_solve, basis flow)
     from dmhomo_b200.compat import pixel_wise_mapping, flow_and_mapping_operations
-    from dmhomo_b200.compat import losses, dgm
+    from dmhomo_b200.compat import losses, dgm, data_loader   # HEM/dataset/data_loader.py helpers
 
 `patch_reference()` rebinds those names inside an already imported reference tree (both
 import roots the reference uses: `HEM.model.utils` and `model.utils`), so HEM training /
@@ -11,7 +11,7 @@ evaluation and DGM sampling pick the kernels up unchanged.
 """
 import sys
 
-from . import dgm, flow_and_mapping_operations, hem_net, hem_utils, losses, pixel_wise_mapping  # noqa: F401
+from . import data_loader, dgm, flow_and_mapping_operations, hem_net, hem_utils, losses, pixel_wise_mapping  # noqa: F401
 
 # reference module (either import root) -> (our module, names to rebind)
 _TARGETS = {

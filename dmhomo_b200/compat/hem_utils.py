@@ -142,15 +142,18 @@ def get_warp_flow(img, flow, start=0):
 
 
 def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False, align_corners=True):
-    """HEM/model/utils.py:556-572 (scales `inputs` in place when if_rate, as the reference)."""
+    """HEM/model/utils.py:556-572 (scales `inputs` in place when if_rate, as the reference: callers see it)."""
     _, _, h, w = target_as.size()
     if if_rate:
         _, _, h_, w_ = inputs.size()
         inputs[:, 0, :, :] *= (w / w_)
         inputs[:, 1, :, :] *= (h / h_)
-    if mode == "nearest":
-        return F.interpolate(inputs, [h, w], mode=mode)
-    return F.interpolate(inputs, [h, w], mode=mode, align_corners=align_corners)
+    if mode != "bilinear" or inputs.shape[1] != 2:
+        # nearest / other channel counts: not on the hot path (no caller in the reference's active configuration)
+        if mode == "nearest":
+            return F.interpolate(inputs, [h, w], mode=mode)
+        return F.interpolate(inputs, [h, w], mode=mode, align_corners=align_corners)
+    return ops.flow_upsample(inputs, (h, w), if_rate=False, align_corners=align_corners)
 
 
 def gen_basis(h, w, is_qr=True, is_scale=True):

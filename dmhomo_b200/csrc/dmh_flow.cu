@@ -111,9 +111,14 @@ __global__ void __launch_bounds__(kThreads) h2flow_f64_kernel(const double* __re
     const double Y = __dadd_rn(__dadd_rn(__dmul_rn(hm[3], dx), __dmul_rn(hm[4], dy)), hm[5]);
     const double T = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(hm[6], dx), __dmul_rn(hm[7], dy)), hm[8]), eps);
     double ox = __ddiv_rn(X, T), oy = __ddiv_rn(Y, T);
-    if (!as_mapping) {
+    if (as_mapping == 0) {
       ox = __dsub_rn(ox, dx);
       oy = __dsub_rn(oy, dy);
+    } else if (as_mapping == 2) {
+      // homo_convert_to_flow (HEM/dataset/data_loader.py:42-52): the mapping is rounded to fp32 first
+      // (map_x.astype(np.float32)), then convert_mapping_to_flow subtracts the fp32 grid in fp32
+      ox = (double)__fsub_rn((float)ox, (float)x);
+      oy = (double)__fsub_rn((float)oy, (float)y);
     }
     if (channels_last) {
       reinterpret_cast<float2*>(out)[i] = make_float2((float)ox, (float)oy);

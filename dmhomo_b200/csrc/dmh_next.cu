@@ -1,0 +1,220 @@
+// The data formats either side of the warp path:
+//
+//  * pairs_u8_kernel      the on-disk pair format {"img12": (6,H,W) uint8} -> what the HEM loader hands the
+//                         network: normalised grey full images, the crop patch, and the /255 RGB pair
+//                         (HEM/dataset/data_loader.py:121-146, 217-255; generate_nyps_to_single_case.py:29-47);
+//  * flow_upsample_*      upsample2d_flow_as(flow, target, if_rate) - bilinear, align_corners, optional rate
+//                         scaling - and its adjoint, the step between the basis flow and the pyramid-level feature
+//                         warp inside the backbone (HEM/model/utils.py:556-572, swin_multi.py:161-166, 1175-1182).
+//
+// Both are one-pass, coalesced, HBM-bound elementwise kernels (grid-stride over a bounded grid).
+#include "dmh_common.cuh"
+
+namespace dmh {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(long long n) {
+  long long b = (n + kThreads - 1) / kThreads;
+  const long long cap = (long long)kNumSMs * 16;
+  return (unsigned)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+struct PairNorm {
+  double mean[3], std[3];
+};
+
+// grey = float32( ((n0 + n1) + n2) / 3 ), n_c = (u8_c - mean_c) / std_c in fp64: numpy's `(img - mean_I) / std_I`
+// followed by `np.mean(axis=2)` (left-associated add.reduce, then a true division by the count) and torch.Tensor().
+__device__ __forceinline__ float grey_of(unsigned r, unsigned g, unsigned b, const PairNorm& nm) {
+  const double n0 = __ddiv_rn(__dsub_rn((double)r, nm.mean[0]), nm.std[0]);
+  const double n1 = __ddiv_rn(__dsub_rn((double)g, nm.mean[1]), nm.std[1]);
+  const double n2 = __ddiv_rn(__dsub_rn((double)b, nm.mean[2]), nm.std[2]);
+  return (float)__ddiv_rn(__dadd_rn(__dadd_rn(n0, n1), n2), 3.0);
+}
+
+// One thread = four consecutive pixels of one sample (W % 4 == 0): six uchar4 loads, float4 stores.
+__global__ void __launch_bounds__(kThreads) pairs_u8_kernel(const uint8_t* __restrict__ img12, const int* __restrict__ start,
+                                                            float* __restrict__ grey_full, float* __restrict__ grey_patch,
+                                                            float* __restrict__ rgb_full, const __grid_constant__ PairNorm nm,
+                                                            int B, int H, int W, int ph, int pw) {
+  const long long plane = (long long)H * W, quads = plane / 4, total = quads * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / quads);
+    const long long q = i - (long long)b * quads;
+    const long long p = q * 4;
+    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+    const uint8_t* src = img12 + (size_t)b * 6 * plane + p;
+    uchar4 ch[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ch[c] = __ldg(reinterpret_cast<const uchar4*>(src + (size_t)c * plane));
+    float4 g1, g2;
+    g1.x = grey_of(ch[0].x, ch[1].x, ch[2].x, nm); g1.y = grey_of(ch[0].y, ch[1].y, ch[2].y, nm);
+    g1.z = grey_of(ch[0].z, ch[1].z, ch[2].z, nm); g1.w = grey_of(ch[0].w, ch[1].w, ch[2].w, nm);
+    g2.x = grey_of(ch[3].x, ch[4].x, ch[5].x, nm); g2.y = grey_of(ch[3].y, ch[4].y, ch[5].y, nm);
+    g2.z = grey_of(ch[3].z, ch[4].z, ch[5].z, nm); g2.w = grey_of(ch[3].w, ch[4].w, ch[5].w, nm);
+    if (grey_full) {
+      float* o = grey_full + (size_t)b * 2 * plane + p;
+      *reinterpret_cast<float4*>(o) = g1;
+      *reinterpret_cast<float4*>(o + plane) = g2;
+    }
+    if (rgb_full) {   // torch.Tensor(uint8 image).float() / 255.
+      float* o = rgb_full + (size_t)b * 6 * plane + p;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        *reinterpret_cast<float4*>(o + (size_t)c * plane) =
+            make_float4(__fdiv_rn((float)ch[c].x, 255.f), __fdiv_rn((float)ch[c].y, 255.f), __fdiv_rn((float)ch[c].z, 255.f),
+                        __fdiv_rn((float)ch[c].w, 255.f));
+    }
+    if (grey_patch) {   // img[y0 : y0 + ph, x0 : x0 + pw] of the grey images (random_crop_tt)
+      const int x0 = __ldg(start + 2 * b), y0 = __ldg(start + 2 * b + 1);
+      const int py = y - y0;
+      if (py >= 0 && py < ph) {
+        float* o = grey_patch + (size_t)b * 2 * ph * pw + (size_t)py * pw;
+        const float v1[4] = {g1.x, g1.y, g1.z, g1.w}, v2[4] = {g2.x, g2.y, g2.z, g2.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int px = x + k - x0;
+          if (px >= 0 && px < pw) {
+            o[px] = v1[k];
+            o[(size_t)ph * pw + px] = v2[k];
+          }
+        }
+      }
+    }
+  }
+}
+
+// torch's upsample_bilinear2d source index (align_corners: scale * dst with scale = (in - 1) / (out - 1) in fp32;
+// otherwise scale * (dst + 0.5) - 0.5 clamped at 0 with scale = in / out), index clamp and lambda.
+__device__ __forceinline__ void src_index(int dst, int in_size, float scale, bool align, int& i0, int& i1, float& l0, float& l1) {
+  float real = align ? scale * (float)dst : fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)real, in_size - 1);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = fminf(fmaxf(real - (float)i0, 0.f), 1.f);
+  l0 = 1.f - l1;
+}
+
+// out[b, c, y, x] = rate_c * bilinear(in[b, c]), c = 0: horizontal flow (rate_x), c = 1: vertical flow (rate_y)
+__global__ void __launch_bounds__(kThreads) flow_upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                                     int hi, int wi, int ho, int wo, float sy, float sx,
+                                                                     float rate_x, float rate_y, int align) {
+  const long long plane = (long long)ho * wo, total = plane * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane);
+    const long long p = i - (long long)b * plane;
+    const int y = (int)(p / wo), x = (int)(p - (long long)y * wo);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(y, hi, sy, align != 0, y0, y1, ly0, ly1);
+    src_index(x, wi, sx, align != 0, x0, x1, lx0, lx1);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float* s = in + ((size_t)b * 2 + c) * hi * wi;
+      const float r = c ? rate_y : rate_x;
+      // the in-place `inputs[:, c] *= rate` of the reference happens before the interpolation
+      const float a = mul_rn(__ldg(s + (size_t)y0 * wi + x0), r), bq = mul_rn(__ldg(s + (size_t)y0 * wi + x1), r);
+      const float cq = mul_rn(__ldg(s + (size_t)y1 * wi + x0), r), d = mul_rn(__ldg(s + (size_t)y1 * wi + x1), r);
+      out[((size_t)b * 2 + c) * plane + p] = ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);
+    }
+  }
+}
+
+// adjoint: grad_in[b, c, yi, xi] = rate_c * sum over the output pixels whose footprint contains (yi, xi).
+// Gather form (no atomics): one thread per INPUT pixel walks the output rows / columns that map near it; with
+// align_corners the outputs touching input row yi lie in (yi - 1, yi + 1) / scale.
+__global__ void __launch_bounds__(kThreads) flow_upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int B,
+                                                                     int hi, int wi, int ho, int wo, float sy, float sx,
+                                                                     float rate_x, float rate_y, int align) {
+  const long long plane_i = (long long)hi * wi, total = plane_i * B;
+  const long long plane_o = (long long)ho * wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / plane_i);
+    const long long p = i - (long long)b * plane_i;
+    const int yi = (int)(p / wi), xi = (int)(p - (long long)yi * wi);
+    // candidate output range: the outputs whose source coordinate lies in (yi - 1, yi + 1), two pixels of slack, the
+    // clamped ends widened to the border; every candidate is verified through src_index itself
+    const float isy = (sy > 0.f) ? 1.f / sy : (float)ho, isx = (sx > 0.f) ? 1.f / sx : (float)wo;
+    const float oy = align ? 0.f : 0.5f, ox = align ? 0.f : 0.5f;   // real = s * (dst + o) - o
+    int ya = (int)floorf(((float)yi - 1.f + oy) * isy - oy) - 2, yb = (int)ceilf(((float)yi + 1.f + oy) * isy - oy) + 2;
+    int xa = (int)floorf(((float)xi - 1.f + ox) * isx - ox) - 2, xb = (int)ceilf(((float)xi + 1.f + ox) * isx - ox) + 2;
+    if (yi == 0) ya = 0;
+    if (yi == hi - 1) yb = ho - 1;
+    if (xi == 0) xa = 0;
+    if (xi == wi - 1) xb = wo - 1;
+    ya = max(ya, 0); yb = min(yb, ho - 1); xa = max(xa, 0); xb = min(xb, wo - 1);
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int y = ya; y <= yb; ++y) {
+      int y0, y1;
+      float ly0, ly1;
+      src_index(y, hi, sy, align != 0, y0, y1, ly0, ly1);
+      const float wy = ((y0 == yi) ? ly0 : 0.f) + ((y1 == yi) ? ly1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xa; x <= xb; ++x) {
+        int x0, x1;
+        float lx0, lx1;
+        src_index(x, wi, sx, align != 0, x0, x1, lx0, lx1);
+        const float wx = ((x0 == xi) ? lx0 : 0.f) + ((x1 == xi) ? lx1 : 0.f);
+        if (wx == 0.f) continue;
+        const float wgt = wy * wx;
+        acc0 = fmaf(wgt, __ldg(gout + ((size_t)b * 2) * plane_o + (size_t)y * wo + x), acc0);
+        acc1 = fmaf(wgt, __ldg(gout + ((size_t)b * 2 + 1) * plane_o + (size_t)y * wo + x), acc1);
+      }
+    }
+    gin[((size_t)b * 2) * plane_i + p] = acc0 * rate_x;
+    gin[((size_t)b * 2 + 1) * plane_i + p] = acc1 * rate_y;
+  }
+}
+
+float scale_of(int in, int out, bool align) {
+  if (align) return (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  return (float)in / (float)out;
+}
+
+}  // namespace
+}  // namespace dmh
+
+extern "C" int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, float* gray_full, float* gray_patch, float* rgb_full,
+                                    const double* mean3, const double* std3, int B, int H, int W, int patch_h, int patch_w,
+                                    void* stream) {
+  DMH_REQUIRE(img12 && mean3 && std3, "pairs_u8_to_gray: null pointer");
+  DMH_REQUIRE(gray_full || gray_patch || rgb_full, "pairs_u8_to_gray: no output requested");
+  DMH_REQUIRE(B > 0 && H > 0 && W > 0, "pairs_u8_to_gray: non-positive size");
+  DMH_REQUIRE((W & 3) == 0, "pairs_u8_to_gray: W must be a multiple of 4 (got %d)", W);
+  DMH_REQUIRE(!gray_patch || (start && patch_h > 0 && patch_w > 0), "pairs_u8_to_gray: a patch needs start (B,2) and a size");
+  dmh::PairNorm nm;
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = mean3[c];
+    nm.std[c] = std3[c];
+    DMH_REQUIRE(std3[c] != 0.0, "pairs_u8_to_gray: std[%d] is zero", c);
+  }
+  const long long total = (long long)B * H * W / 4;
+  dmh::pairs_u8_kernel<<<dmh::grid_for(total), dmh::kThreads, 0, dmh::as_stream(stream)>>>(img12, start, gray_full, gray_patch,
+                                                                                        rgb_full, nm, B, H, W, patch_h, patch_w);
+  return dmh::launched("pairs_u8_kernel");
+}
+
+extern "C" int dmh_flow_upsample(const float* flow, float* out, int B, int hi, int wi, int ho, int wo, int if_rate,
+                                 int align_corners, void* stream) {
+  DMH_REQUIRE(flow && out, "flow_upsample: null pointer");
+  DMH_REQUIRE(B > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0, "flow_upsample: non-positive size");
+  const bool al = align_corners != 0;
+  // Python float division w / w_ is fp64; the in-place multiply of an fp32 tensor rounds the scalar to fp32 first
+  const float rx = if_rate ? (float)((double)wo / (double)wi) : 1.f, ry = if_rate ? (float)((double)ho / (double)hi) : 1.f;
+  dmh::flow_upsample_fwd_kernel<<<dmh::grid_for((long long)B * ho * wo), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
+      flow, out, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
+  return dmh::launched("flow_upsample_fwd_kernel");
+}
+
+extern "C" int dmh_flow_upsample_backward(const float* grad_out, float* grad_flow, int B, int hi, int wi, int ho, int wo,
+                                          int if_rate, int align_corners, void* stream) {
+  DMH_REQUIRE(grad_out && grad_flow, "flow_upsample_backward: null pointer");
+  DMH_REQUIRE(B > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0, "flow_upsample_backward: non-positive size");
+  const bool al = align_corners != 0;
+  const float rx = if_rate ? (float)((double)wo / (double)wi) : 1.f, ry = if_rate ? (float)((double)ho / (double)hi) : 1.f;
+  dmh::flow_upsample_bwd_kernel<<<dmh::grid_for((long long)B * hi * wi), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
+      grad_out, grad_flow, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
+  return dmh::launched("flow_upsample_bwd_kernel");
+}

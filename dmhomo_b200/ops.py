@@ -201,7 +201,9 @@ def homography_to_flow(H, h, w, divide=1, start=0):
 def homography_to_flow_f64(H, h, w, eps=1e-6, channels_last=True, as_mapping=False):
     """homo_to_flow()/get_flow_np() (ddpm.py:913-975; eps=1e-6) and
     from_homography_to_pixel_wise_mapping() (flow_and_mapping_operations.py:454-484; eps=1e-8,
-    as_mapping=True): fp64 arithmetic, fp32 result.  H: (B,3,3) float64 CUDA tensor."""
+    as_mapping=True): fp64 arithmetic, fp32 result.  as_mapping=2: the loaders' ground-truth flow
+    homo_convert_to_flow (HEM/dataset/data_loader.py:42-52) = fl32(fl32(mapping) - grid).
+    H: (B,3,3) float64 CUDA tensor."""
     dev = _cuda(H)
     Hc = H.to(torch.float64).contiguous()
     B = Hc.numel() // 9
@@ -708,3 +710,69 @@ def flow_to_homography_ls(flow):
         L.check(L.lib().dmh_flow_to_homography_ls(_p(f), _p(H), _p(ws), B, h, w, _stream(dev)),
                 "flow_to_homography_ls")
     return H
+
+
+# ----------------------------------------------------------------------------------------------
+# data formats either side of the path
+# ----------------------------------------------------------------------------------------------
+MEAN_I = (118.93, 113.97, 102.60)   # HEM/dataset/data_loader.py:103-104
+STD_I = (69.85, 68.81, 72.45)
+
+
+def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEAN_I, std=STD_I):
+    """The on-disk pair format batched as uint8 (B,6,H,W) (CUDA) -> (imgs_gray_full (B,2,H,W), imgs_gray_patch
+    (B,2,ph,pw) or None, imgs_rgb_full (B,6,H,W) or None) exactly as DGMTrainData.__getitem__ / data_aug produce them
+    on the host in numpy fp64 (HEM/dataset/data_loader.py:121-146, 217-255).  start: (B,2) int (x, y) crop origins."""
+    dev = _cuda(img12)
+    if img12.dtype != torch.uint8 or img12.dim() != 4 or img12.shape[1] != 6:
+        raise ValueError("pairs_u8_to_gray: img12 must be uint8 (B,6,H,W)")
+    x = img12.contiguous()
+    B, _, H, W = x.shape
+    full = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
+    rgb = torch.empty(B, 6, H, W, device=dev, dtype=torch.float32) if want_rgb else None
+    patch, st, ph, pw = None, None, 0, 0
+    if patch_size is not None:
+        if start is None:
+            raise ValueError("pairs_u8_to_gray: a patch needs start (B,2)")
+        ph, pw = int(patch_size[0]), int(patch_size[1])
+        st = torch.as_tensor(start, device=dev).to(torch.int32).reshape(B, 2).contiguous()
+        if bool(((st[:, 0] < 0) | (st[:, 0] + pw > W) | (st[:, 1] < 0) | (st[:, 1] + ph > H)).any()):
+            raise ValueError("pairs_u8_to_gray: crop window outside the image")
+        patch = torch.empty(B, 2, ph, pw, device=dev, dtype=torch.float32)
+    m3, s3 = (C.c_double * 3)(*[float(v) for v in mean]), (C.c_double * 3)(*[float(v) for v in std])
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_pairs_u8_to_gray(_p(x), _p(st), _p(full), _p(patch), _p(rgb), m3, s3, B, H, W, ph, pw,
+                                             _stream(dev)), "pairs_u8_to_gray")
+    return full, patch, rgb
+
+
+class _FlowUpsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, ho, wo, if_rate, align_corners):
+        dev = _cuda(flow)
+        f = _f32(flow)
+        if f.dim() != 4 or f.shape[1] != 2:
+            raise ValueError("flow_upsample: flow must be (B,2,h,w)")
+        B, _, hi, wi = f.shape
+        out = torch.empty(B, 2, ho, wo, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_flow_upsample(_p(f), _p(out), B, hi, wi, ho, wo, int(if_rate), int(align_corners),
+                                              _stream(dev)), "flow_upsample")
+        ctx.cfg = (B, hi, wi, ho, wo, int(if_rate), int(align_corners))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, hi, wi, ho, wo, if_rate, align = ctx.cfg
+        gc = _f32(g)
+        gin = torch.empty(B, 2, hi, wi, device=gc.device, dtype=torch.float32)
+        with torch.cuda.device(gc.device):
+            L.check(L.lib().dmh_flow_upsample_backward(_p(gc), _p(gin), B, hi, wi, ho, wo, if_rate, align,
+                                                       _stream(gc.device)), "flow_upsample_backward")
+        return gin, None, None, None, None
+
+
+def flow_upsample(flow, size, if_rate=False, align_corners=True):
+    """upsample2d_flow_as without the in-place side effect: bilinear resize of a flow field (B,2,h,w) to `size`
+    = (ho, wo); if_rate scales channel 0 by wo/w and channel 1 by ho/h (HEM/model/utils.py:556-572)."""
+    return _FlowUpsample.apply(flow, int(size[0]), int(size[1]), bool(if_rate), bool(align_corners))

@@ -173,9 +173,29 @@ DMH_API int dmh_homography_to_flow_backward(const float* H, const float* grad_fl
  * T + eps always, rounded to fp32 at the end.  ddpm.py:913-975;
  * HEM/utils_operations/flow_and_mapping_operations.py:454-484.
  * H: (B,3,3) double.  out: channels_last ? (B,h,w,2) : (B,2,h,w).
- * as_mapping: write q/T (mapping) instead of q/T - grid (flow). */
+ * as_mapping: 0 = flow q/T - grid rounded once; 1 = mapping q/T; 2 = the loaders' ground-truth flow
+ * homo_convert_to_flow(H, size) = fl32(fl32(q/T) - grid) (HEM/dataset/data_loader.py:42-52, eps 1e-8). */
 DMH_API int dmh_homography_to_flow_f64(const double* H, float* out, int B, int h, int w, double eps,
                                int channels_last, int as_mapping, void* stream);
+
+/* --- data formats either side of the path ------------------------ */
+/* The on-disk pair format {"img12": (6,H,W) uint8} batched as (B,6,H,W) -> what DGMTrainData.__getitem__ /
+ * data_aug hand the network (HEM/dataset/data_loader.py:121-146, 217-255): gray_full (B,2,H,W) =
+ * float32(mean_c((u8 - mean_c) / std_c)) in fp64 (numpy), gray_patch (B,2,ph,pw) = its crop at start[b] = (x, y)
+ * (int32, (B,2)), rgb_full (B,6,H,W) = float32(u8) / 255.  Any output may be null.  W % 4 == 0.
+ * mean3 / std3 are HOST pointers to three doubles. */
+DMH_API int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, float* gray_full, float* gray_patch,
+                         float* rgb_full, const double* mean3, const double* std3, int B, int H, int W,
+                         int patch_h, int patch_w, void* stream);
+/* upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate, align_corners)
+ * (HEM/model/utils.py:556-572; swin_multi.py:1175-1182): flow (B,2,hi,wi) -> out (B,2,ho,wo), bilinear with
+ * torch's index / lambda rules; if_rate multiplies channel 0 by wo/wi and channel 1 by ho/hi first (the
+ * reference does that in place on its input - the compat layer reproduces the side effect). */
+DMH_API int dmh_flow_upsample(const float* flow, float* out, int B, int hi, int wi, int ho, int wo, int if_rate,
+                      int align_corners, void* stream);
+/* Adjoint of dmh_flow_upsample: grad_out (B,2,ho,wo) -> grad_flow (B,2,hi,wi) WRITTEN (gather form, no atomics). */
+DMH_API int dmh_flow_upsample_backward(const float* grad_out, float* grad_flow, int B, int hi, int wi, int ho,
+                               int wo, int if_rate, int align_corners, void* stream);
 
 /* --- basis flows (A12) ------------------------------------------------------------------ */
 /* flow = sum_k w_k basis_k.  basis (8,2,h,w), weight (B,8) -> flow (B,2,h,w). */

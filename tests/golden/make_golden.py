@@ -4,7 +4,7 @@ on small seeded inputs.  Only runnable in the build container; the fixtures it w
 that the oracle and the CUDA path can be checked against the reference's own outputs anywhere
 (the GPU box has no /root/reference).
 
-    CUDA_VISIBLE_DEVICES="" python tests/golden/make_golden.py
+    CUDA_VISIBLE_DEVICES="" python tests/golden/make_golden.py [fixture names ...]
 
 Every array is stored with the inputs that produced it, so a test never has to re-derive inputs.
 """
@@ -30,7 +30,12 @@ def corners(B, h, w):
     return c.view(1, 4, 2).repeat(B, 1, 1)
 
 
+ONLY = set(sys.argv[1:])   # optional: fixture names to (re)write; the others are left untouched
+
+
 def save(name, **arrs):
+    if ONLY and name not in ONLY:
+        return
     out = {}
     for k, v in arrs.items():
         out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
@@ -159,6 +164,42 @@ def main():
     pts = torch.rand(3, 6, 2, 2, generator=g(22)) * torch.tensor([29.0, 19.0])
     errs = L.compute_eval_results({"imgs_gray_full": torch.zeros(3, 2, 20, 30), "pt_set": pts}, {"flow_f": ffe, "flow_b": fbe})
     save("eval_points", pts=pts, flow_f=ffe, flow_b=fbe, err=torch.stack([torch.as_tensor(e) for e in errs]))
+
+
+
+    # ---- section 8f rows 2-4: uint8 pair format, loader GT flow, flow upsample ------------------------
+    import types
+    DL = r.data_loader
+    rs = np.random.default_rng(61)
+    Bp, Hp_, Wp_ = 3, 40, 56
+    img12 = rs.integers(0, 256, size=(Bp, 6, Hp_, Wp_), dtype=np.uint8)
+    starts = np.array([[4, 3], [0, 0], [24, 8]], dtype=np.int32)       # [x, y]
+    crop = (32, 32)
+    me = types.SimpleNamespace(mean_I=np.array([118.93, 113.97, 102.60]).reshape(1, 1, 3),
+                               std_I=np.array([69.85, 68.81, 72.45]).reshape(1, 1, 3), crop_size=crop, rho=0)
+    fulls, patches, rgbs = [], [], []
+    for b in range(Bp):
+        hwc = img12[b].transpose(1, 2, 0)
+        i1, i2 = hwc[..., :3], hwc[..., 3:]
+        rgbs.append(torch.cat((torch.Tensor(i1), torch.Tensor(i2)), dim=-1).permute(2, 0, 1).float() / 255.)  # data_loader.py:144-145
+        o = DL.DGMTrainData.data_aug(me, i1, i2, np.eye(3), np.eye(3), start=[int(starts[b, 0]), int(starts[b, 1])])
+        fulls.append(torch.cat((o[0], o[1]), dim=2).permute(2, 0, 1).float())
+        patches.append(torch.cat((o[2], o[3]), dim=2).permute(2, 0, 1).float())
+    save("pairs_u8", img12=img12, start=starts, crop=np.array(crop), gray_full=torch.stack(fulls), gray_patch=torch.stack(patches),
+         rgb_full=torch.stack(rgbs))
+
+    Hg = np.stack([np.eye(3) + rs.normal(size=(3, 3)) * np.array([[2e-2, 2e-2, 3.0], [2e-2, 2e-2, 3.0], [1e-4, 1e-4, 0.0]])
+                   for _ in range(3)])
+    gtf = torch.cat([DL.homo_convert_to_flow(Hg[b], (40, 56)) for b in range(3)], 0)
+    save("gt_flow", H=Hg, flow=gtf, H_scaled=np.stack([DL.homo_scale(360, 640, Hg[b], 40, 56) for b in range(3)]),
+         hw=np.array([40, 56]))
+
+    flo = torch.randn(2, 2, 10, 18, generator=g(62)) * 3
+    ups = {}
+    for name, (ho, wo, rate, al) in {"x4_rate": (40, 72, True, True), "odd_rate": (23, 31, True, True),
+                                     "down": (5, 9, False, True), "x2_norate": (20, 36, False, True)}.items():
+        ups[name] = U.upsample2d_flow_as(flo.clone(), torch.zeros(1, 1, ho, wo), if_rate=rate, align_corners=al)
+    save("upsample", flow=flo, **ups)
 
 
 if __name__ == "__main__":

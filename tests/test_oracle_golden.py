@@ -134,3 +134,32 @@ def test_eval_points_golden():
     d = load("eval_points")
     err = torch.stack(port.eval_point_errors(d["pts"], d["flow_f"], d["flow_b"]))
     assert (err - d["err"]).abs().max().item() < 1e-6
+
+
+# ---- the data formats either side of the path ----------------------------------
+def test_pairs_u8_golden():
+    """The uint8 pair format -> grey full / patch / RGB tensors, against DGMTrainData.data_aug itself."""
+    d = load("pairs_u8")
+    crop = tuple(int(v) for v in d["crop"])
+    for b in range(d["img12"].shape[0]):
+        full, patch, rgb = port.pairs_u8_to_gray(d["img12"][b].numpy(), d["start"][b].tolist(), crop)
+        assert torch.equal(full, d["gray_full"][b])
+        assert torch.equal(patch, d["gray_patch"][b])
+        assert torch.equal(rgb, d["rgb_full"][b])
+
+
+def test_gt_flow_golden():
+    d = load("gt_flow")
+    h, w = [int(v) for v in d["hw"]]
+    for b in range(d["H"].shape[0]):
+        Hm = d["H"][b].numpy()
+        assert torch.equal(port.homo_convert_to_flow(Hm, (h, w))[0], d["flow"][b])
+        assert np.array_equal(port.homo_scale(360, 640, Hm, h, w), d["H_scaled"][b].numpy())
+
+
+def test_upsample_golden():
+    d = load("upsample")
+    fl = d["flow"]
+    for name, (rate,) in {"x4_rate": (True,), "odd_rate": (True,), "down": (False,), "x2_norate": (False,)}.items():
+        tgt = torch.zeros(1, 1, *d[name].shape[-2:])
+        assert torch.equal(port.upsample2d_flow_as(fl, tgt, if_rate=rate), d[name]), name

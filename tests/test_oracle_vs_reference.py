@@ -204,3 +204,20 @@ def test_upsample_flow(ref):
     tgt = torch.zeros(2, 1, 15, 20)
     a = ref.utils.upsample2d_flow_as(fl.clone(), tgt, if_rate=True)
     assert torch.equal(a, port.upsample2d_flow_as(fl, tgt, if_rate=True))
+
+
+def test_pairs_u8_against_data_aug(ref):
+    """oracle restatement of __getitem__ + data_aug vs the reference's own method."""
+    import types
+
+    DL = ref.data_loader
+    rs = np.random.default_rng(3)
+    img12 = rs.integers(0, 256, size=(6, 48, 64), dtype=np.uint8)
+    me = types.SimpleNamespace(mean_I=np.array([118.93, 113.97, 102.60]).reshape(1, 1, 3),
+                               std_I=np.array([69.85, 68.81, 72.45]).reshape(1, 1, 3), crop_size=(24, 40), rho=0)
+    hwc = img12.transpose(1, 2, 0)
+    o = DL.DGMTrainData.data_aug(me, hwc[..., :3], hwc[..., 3:], np.eye(3), np.eye(3), start=[7, 11])
+    full, patch, rgb = port.pairs_u8_to_gray(img12, [7, 11], (24, 40))
+    assert torch.equal(full, torch.cat((o[0], o[1]), dim=2).permute(2, 0, 1).float())
+    assert torch.equal(patch, torch.cat((o[2], o[3]), dim=2).permute(2, 0, 1).float())
+    assert o[8] == [7, 11]
