@@ -43,6 +43,23 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSMs = 148;  // B200
 
+// Elementwise launches over (B, h, w): blockIdx.y walks the samples, blockIdx.x * threads walks one plane, both
+// grid-stride, all index arithmetic in 32 bits (a flat 64-bit index costs two 64-bit divisions per pixel, which
+// is what these kernels then spend their time on: profiles/r1_kernels.txt).  Needs h * w < 2^31.
+inline dim3 plane_grid(long long plane, int B, int threads = 256) {
+  long long gx = (plane + threads - 1) / threads;
+  if (gx > 4096) gx = 4096;
+  if (gx < 1) gx = 1;
+  long long gy = ((long long)kNumSMs * 16 + gx - 1) / gx;
+  if (gy > B) gy = B;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+#define DMH_PLANE_LOOP(b, p, B_, plane_)                 \
+  for (int b = blockIdx.y; b < (B_); b += gridDim.y)     \
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < (unsigned)(plane_); p += gridDim.x * blockDim.x)
+
 // ---- device side ----------------------------------------------------------------------
 // Separately rounded fp32 arithmetic: the reference is a chain of individually rounded
 // ATen elementwise ops, so bit-exact coordinates / indices / masks need "no FMA

@@ -23,24 +23,45 @@ __device__ __forceinline__ void h2flow(const float* hm, float gx, float gy, floa
   fy = sub_rn(div_rn(qY, qT), gy);
 }
 
+// V pixels per thread (V = 4 when w % 4 == 0: the four pixels share a row, stores are 128-bit).
+template <int V>
 __global__ void __launch_bounds__(kThreads) h2flow_fwd_kernel(const float* __restrict__ H, float* __restrict__ flow,
                                                               int B, int h, int w, int dv, float sx, float sy,
                                                               const float* __restrict__ start) {
-  const long long plane = (long long)h * w, total = plane * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
-    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-    const int cell = (dv == 1) ? 0 : (min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1));
-    const float* hp = H + ((size_t)b * dv * dv + cell) * 9;
+  const long long plane = (long long)h * w;
+  const unsigned groups = (unsigned)(plane / V);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     float hm[9];
+    if (dv == 1) {   // one homography per sample: loaded once per sample, not once per pixel
 #pragma unroll
-    for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
-    float fx, fy, qX, qY, qT;
+      for (int k = 0; k < 9; ++k) hm[k] = __ldg(H + (size_t)b * 9 + k);
+    }
     const float ox = start ? __ldg(start + 2 * b) : sx, oy = start ? __ldg(start + 2 * b + 1) : sy;
-    h2flow(hm, add_rn((float)x, ox), add_rn((float)y, oy), fx, fy, qX, qY, qT);
-    flow[((size_t)b * 2) * plane + p] = fx;
-    flow[((size_t)b * 2 + 1) * plane + p] = fy;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += gridDim.x * blockDim.x) {
+      const unsigned p = q * V;
+      const int y = (int)(p / (unsigned)w), x0 = (int)(p - (unsigned)y * (unsigned)w);
+      float fxv[V], fyv[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int x = x0 + v;
+        if (dv != 1) {
+          const int cell = min(y / (h / dv), dv - 1) * dv + min(x / (w / dv), dv - 1);
+          const float* hp = H + ((size_t)b * dv * dv + cell) * 9;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
+        }
+        float qX, qY, qT;
+        h2flow(hm, add_rn((float)x, ox), add_rn((float)y, oy), fxv[v], fyv[v], qX, qY, qT);
+      }
+      float* o = flow + ((size_t)b * 2) * plane + p;
+      if (V == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(fxv[0], fxv[1], fxv[2], fxv[3]);
+        *reinterpret_cast<float4*>(o + plane) = make_float4(fyv[0], fyv[1], fyv[2], fyv[3]);
+      } else {
+        o[0] = fxv[0];
+        o[plane] = fyv[0];
+      }
+    }
   }
 }
 
@@ -97,34 +118,58 @@ __global__ void __launch_bounds__(kThreads) h2flow_bwd_kernel(const float* __res
 }
 
 // ---- A15: numpy fp64 homography -> flow / mapping (ddpm.py:913-975; ...operations.py:454-484) ----
+template <int V>
 __global__ void __launch_bounds__(kThreads) h2flow_f64_kernel(const double* __restrict__ H, float* __restrict__ out,
                                                               int B, int h, int w, double eps, int channels_last,
                                                               int as_mapping) {
-  const long long plane = (long long)h * w, total = plane * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
-    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-    const double* hm = H + (size_t)b * 9;
-    const double dx = (double)x, dy = (double)y;
-    const double X = __dadd_rn(__dadd_rn(__dmul_rn(hm[0], dx), __dmul_rn(hm[1], dy)), hm[2]);
-    const double Y = __dadd_rn(__dadd_rn(__dmul_rn(hm[3], dx), __dmul_rn(hm[4], dy)), hm[5]);
-    const double T = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(hm[6], dx), __dmul_rn(hm[7], dy)), hm[8]), eps);
-    double ox = __ddiv_rn(X, T), oy = __ddiv_rn(Y, T);
-    if (as_mapping == 0) {
-      ox = __dsub_rn(ox, dx);
-      oy = __dsub_rn(oy, dy);
-    } else if (as_mapping == 2) {
-      // homo_convert_to_flow (HEM/dataset/data_loader.py:42-52): the mapping is rounded to fp32 first
-      // (map_x.astype(np.float32)), then convert_mapping_to_flow subtracts the fp32 grid in fp32
-      ox = (double)__fsub_rn((float)ox, (float)x);
-      oy = (double)__fsub_rn((float)oy, (float)y);
-    }
-    if (channels_last) {
-      reinterpret_cast<float2*>(out)[i] = make_float2((float)ox, (float)oy);
-    } else {
-      out[((size_t)b * 2) * plane + p] = (float)ox;
-      out[((size_t)b * 2 + 1) * plane + p] = (float)oy;
+  const long long plane = (long long)h * w;
+  const unsigned groups = (unsigned)(plane / V);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    double hm[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hm[k] = H[(size_t)b * 9 + k];
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += gridDim.x * blockDim.x) {
+      const unsigned p = q * V;
+      const int y = (int)(p / (unsigned)w), x0 = (int)(p - (unsigned)y * (unsigned)w);
+      float oxv[V], oyv[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int x = x0 + v;
+        const double dx = (double)x, dy = (double)y;
+        const double X = __dadd_rn(__dadd_rn(__dmul_rn(hm[0], dx), __dmul_rn(hm[1], dy)), hm[2]);
+        const double Y = __dadd_rn(__dadd_rn(__dmul_rn(hm[3], dx), __dmul_rn(hm[4], dy)), hm[5]);
+        const double T = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(hm[6], dx), __dmul_rn(hm[7], dy)), hm[8]), eps);
+        double ox = __ddiv_rn(X, T), oy = __ddiv_rn(Y, T);
+        if (as_mapping == 0) {
+          ox = __dsub_rn(ox, dx);
+          oy = __dsub_rn(oy, dy);
+        } else if (as_mapping == 2) {
+          // homo_convert_to_flow (HEM/dataset/data_loader.py:42-52): the mapping is rounded to fp32 first
+          // (map_x.astype(np.float32)), then convert_mapping_to_flow subtracts the fp32 grid in fp32
+          ox = (double)__fsub_rn((float)ox, (float)x);
+          oy = (double)__fsub_rn((float)oy, (float)y);
+        }
+        oxv[v] = (float)ox;
+        oyv[v] = (float)oy;
+      }
+      if (channels_last) {
+        float2* o = reinterpret_cast<float2*>(out) + (size_t)b * plane + p;
+        if (V == 4) {
+          *reinterpret_cast<float4*>(o) = make_float4(oxv[0], oyv[0], oxv[1], oyv[1]);
+          *reinterpret_cast<float4*>(o + 2) = make_float4(oxv[V - 2], oyv[V - 2], oxv[V - 1], oyv[V - 1]);
+        } else {
+          o[0] = make_float2(oxv[0], oyv[0]);
+        }
+      } else {
+        float* o = out + ((size_t)b * 2) * plane + p;
+        if (V == 4) {
+          *reinterpret_cast<float4*>(o) = make_float4(oxv[0], oxv[1], oxv[V - 2], oxv[V - 1]);
+          *reinterpret_cast<float4*>(o + plane) = make_float4(oyv[0], oyv[1], oyv[V - 2], oyv[V - 1]);
+        } else {
+          o[0] = oxv[0];
+          o[plane] = oyv[0];
+        }
+      }
     }
   }
 }
@@ -191,28 +236,47 @@ __global__ void __launch_bounds__(kThreads) basis_combine_bwd_kernel(const float
 }
 
 // ---- A10/A11: masks (HEM/utils_operations/flow_and_mapping_operations.py:6-71) -----------------------
+template <int V>
 __global__ void __launch_bounds__(kThreads) border_mask_kernel(const float* __restrict__ flow, uint8_t* __restrict__ m8,
                                                                float* __restrict__ mf, int B, int h, int w) {
-  const long long plane = (long long)h * w, total = plane * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
-    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-    const float mx = add_rn(__ldg(flow + ((size_t)b * 2) * plane + p), (float)x);
-    const float my = add_rn(__ldg(flow + ((size_t)b * 2 + 1) * plane + p), (float)y);
-    const bool ok = (mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h);
-    if (m8) m8[i] = ok ? 1 : 0;
-    if (mf) mf[i] = ok ? 1.f : 0.f;
+  const long long plane = (long long)h * w;
+  const unsigned groups = (unsigned)(plane / V);
+  DMH_PLANE_LOOP(b, q, B, groups) {
+    const unsigned p = q * V;
+    const long long i = (long long)b * plane + p;
+    const int y = (int)(p / (unsigned)w), x0 = (int)(p - (unsigned)y * (unsigned)w);
+    float fx[V], fy[V];
+    const float* f = flow + ((size_t)b * 2) * plane + p;
+    if (V == 4) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(f)), b4 = __ldg(reinterpret_cast<const float4*>(f + plane));
+      fx[0] = a4.x; fx[1] = a4.y; fx[V - 2] = a4.z; fx[V - 1] = a4.w;
+      fy[0] = b4.x; fy[1] = b4.y; fy[V - 2] = b4.z; fy[V - 1] = b4.w;
+    } else {
+      fx[0] = __ldg(f);
+      fy[0] = __ldg(f + plane);
+    }
+    uint8_t ok[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float mx = add_rn(fx[v], (float)(x0 + v)), my = add_rn(fy[v], (float)y);
+      ok[v] = ((mx >= 0.f) && (mx <= (float)w) && (my >= 0.f) && (my <= (float)h)) ? 1 : 0;
+    }
+    if (V == 4) {
+      if (m8) *reinterpret_cast<uchar4*>(m8 + i) = make_uchar4(ok[0], ok[1], ok[V - 2], ok[V - 1]);
+      if (mf) *reinterpret_cast<float4*>(mf + i) = make_float4((float)ok[0], (float)ok[1], (float)ok[V - 2], (float)ok[V - 1]);
+    } else {
+      if (m8) m8[i] = ok[0];
+      if (mf) mf[i] = (float)ok[0];
+    }
   }
 }
 
 __global__ void __launch_bounds__(kThreads) zero_border_mask_kernel(const float* __restrict__ img,
                                                                     uint8_t* __restrict__ mask, int B, int h, int w,
                                                                     float eps) {
-  const long long plane = (long long)h * w, total = plane * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
+  const long long plane = (long long)h * w;
+  DMH_PLANE_LOOP(b, p, B, plane) {
+    const long long i = (long long)b * plane + p;   // flat pixel index (channels-last / per-sample-plane layouts)
     const float* ip = img + (size_t)b * 3 * plane + p;
     const bool occ = (__ldg(ip) <= eps) && (__ldg(ip + plane) <= eps) && (__ldg(ip + 2 * plane) <= eps);
     mask[i] = occ ? 0 : 1;
@@ -292,11 +356,10 @@ __global__ void __launch_bounds__(kThreads) scale_inplace_kernel(float* __restri
 __global__ void __launch_bounds__(kThreads) flow_to_rgb_kernel(const float* __restrict__ flow, float* __restrict__ rgb,
                                                                int B, int h, int w, float max_flow, int in_cl,
                                                                int out_cl) {
-  const long long plane = (long long)h * w, total = plane * B;
+  const long long plane = (long long)h * w;
   const float two_pi = 6.2831855f;  // float32(2*np.pi)
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
+  DMH_PLANE_LOOP(b, p, B, plane) {
+    const long long i = (long long)b * plane + p;   // flat pixel index (channels-last / per-sample-plane layouts)
     float u, v;
     if (in_cl) {
       const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
@@ -381,8 +444,12 @@ extern "C" int dmh_homography_to_flow(const float* H, float* flow, int B, int h,
   DMH_REQUIRE(H && flow, "homography_to_flow: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0 && divide >= 1, "homography_to_flow: bad size");
   DMH_REQUIRE(h % divide == 0 && w % divide == 0, "homography_to_flow: h,w must be divisible by divide");
-  h2flow_fwd_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(H, flow, B, h, w, divide,
-                                                                                         start_x, start_y, start);
+  if ((w & 3) == 0 && (reinterpret_cast<uintptr_t>(flow) & 15) == 0)
+    h2flow_fwd_kernel<4><<<plane_grid((long long)h * w / 4, B), kThreads, 0, as_stream(stream)>>>(H, flow, B, h, w, divide,
+                                                                                                start_x, start_y, start);
+  else
+    h2flow_fwd_kernel<1><<<plane_grid((long long)h * w, B), kThreads, 0, as_stream(stream)>>>(H, flow, B, h, w, divide,
+                                                                                            start_x, start_y, start);
   return launched("h2flow_fwd_kernel");
 }
 
@@ -406,8 +473,12 @@ extern "C" int dmh_homography_to_flow_f64(const double* H, float* out, int B, in
                                           int channels_last, int as_mapping, void* stream) {
   DMH_REQUIRE(H && out, "homography_to_flow_f64: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0, "homography_to_flow_f64: bad size");
-  h2flow_f64_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(H, out, B, h, w, eps,
-                                                                                         channels_last, as_mapping);
+  if ((w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    h2flow_f64_kernel<4><<<plane_grid((long long)h * w / 4, B), kThreads, 0, as_stream(stream)>>>(H, out, B, h, w, eps,
+                                                                                                channels_last, as_mapping);
+  else
+    h2flow_f64_kernel<1><<<plane_grid((long long)h * w, B), kThreads, 0, as_stream(stream)>>>(H, out, B, h, w, eps,
+                                                                                            channels_last, as_mapping);
   return launched("h2flow_f64_kernel");
 }
 
@@ -442,15 +513,19 @@ extern "C" int dmh_border_mask(const float* flow, uint8_t* mask_u8, float* mask_
                                void* stream) {
   DMH_REQUIRE(flow && (mask_u8 || mask_f32), "border_mask: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0, "border_mask: bad size");
-  border_mask_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(flow, mask_u8, mask_f32, B,
-                                                                                          h, w);
+  const bool vec = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(flow) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask_u8) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(mask_f32) & 15) == 0;
+  if (vec)
+    border_mask_kernel<4><<<plane_grid((long long)h * w / 4, B), kThreads, 0, as_stream(stream)>>>(flow, mask_u8, mask_f32, B, h, w);
+  else
+    border_mask_kernel<1><<<plane_grid((long long)h * w, B), kThreads, 0, as_stream(stream)>>>(flow, mask_u8, mask_f32, B, h, w);
   return launched("border_mask_kernel");
 }
 
 extern "C" int dmh_zero_border_mask(const float* image, uint8_t* mask, int B, int h, int w, float eps, void* stream) {
   DMH_REQUIRE(image && mask, "zero_border_mask: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0, "zero_border_mask: bad size");
-  zero_border_mask_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(image, mask, B, h, w,
+  zero_border_mask_kernel<<<plane_grid((long long)h * w, B), kThreads, 0, as_stream(stream)>>>(image, mask, B, h, w,
                                                                                                eps);
   return launched("zero_border_mask_kernel");
 }
@@ -499,7 +574,7 @@ extern "C" int dmh_flow_to_rgb(const float* flow, float* rgb, int B, int h, int 
   DMH_REQUIRE(flow && rgb, "flow_to_rgb: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0, "flow_to_rgb: bad size");
   DMH_REQUIRE(max_flow > 0.f, "flow_to_rgb: max_flow must be positive");
-  flow_to_rgb_kernel<<<blocks_for((long long)B * h * w), kThreads, 0, as_stream(stream)>>>(
+  flow_to_rgb_kernel<<<plane_grid((long long)h * w, B), kThreads, 0, as_stream(stream)>>>(
       flow, rgb, B, h, w, max_flow, in_channels_last, out_channels_last);
   return launched("flow_to_rgb_kernel");
 }

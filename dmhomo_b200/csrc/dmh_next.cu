@@ -16,45 +16,44 @@ namespace {
 
 constexpr int kThreads = 256;
 
-inline unsigned grid_for(long long n) {
-  long long b = (n + kThreads - 1) / kThreads;
-  const long long cap = (long long)kNumSMs * 16;
-  return (unsigned)(b < 1 ? 1 : (b < cap ? b : cap));
-}
-
 struct PairNorm {
   double mean[3], std[3];
 };
 
 // grey = float32( ((n0 + n1) + n2) / 3 ), n_c = (u8_c - mean_c) / std_c in fp64: numpy's `(img - mean_I) / std_I`
 // followed by `np.mean(axis=2)` (left-associated add.reduce, then a true division by the count) and torch.Tensor().
-__device__ __forceinline__ float grey_of(unsigned r, unsigned g, unsigned b, const PairNorm& nm) {
-  const double n0 = __ddiv_rn(__dsub_rn((double)r, nm.mean[0]), nm.std[0]);
-  const double n1 = __ddiv_rn(__dsub_rn((double)g, nm.mean[1]), nm.std[1]);
-  const double n2 = __ddiv_rn(__dsub_rn((double)b, nm.mean[2]), nm.std[2]);
-  return (float)__ddiv_rn(__dadd_rn(__dadd_rn(n0, n1), n2), 3.0);
-}
-
+// n_c takes 256 values per channel: every CTA tabulates them once in shared memory (768 fp64 divisions per CTA
+// instead of six per pixel), and float32(u8) / 255 likewise.
 // One thread = four consecutive pixels of one sample (W % 4 == 0): six uchar4 loads, float4 stores.
 __global__ void __launch_bounds__(kThreads) pairs_u8_kernel(const uint8_t* __restrict__ img12, const int* __restrict__ start,
                                                             float* __restrict__ grey_full, float* __restrict__ grey_patch,
                                                             float* __restrict__ rgb_full, const __grid_constant__ PairNorm nm,
                                                             int B, int H, int W, int ph, int pw) {
-  const long long plane = (long long)H * W, quads = plane / 4, total = quads * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / quads);
-    const long long q = i - (long long)b * quads;
-    const long long p = q * 4;
-    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+  __shared__ double lut[3][256];
+  __shared__ float lut255[256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, v = t & 255;
+    lut[c][v] = __ddiv_rn(__dsub_rn((double)v, nm.mean[c]), nm.std[c]);
+  }
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) lut255[t] = __fdiv_rn((float)t, 255.f);
+  __syncthreads();
+  auto grey_of = [&](unsigned r, unsigned g, unsigned bb) -> float {
+    return (float)__ddiv_rn(__dadd_rn(__dadd_rn(lut[0][r], lut[1][g]), lut[2][bb]), 3.0);
+  };
+  const long long plane = (long long)H * W;
+  const unsigned quads = (unsigned)(plane / 4);
+  DMH_PLANE_LOOP(b, q, B, quads) {
+    const unsigned p = q * 4u;
+    const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
     const uint8_t* src = img12 + (size_t)b * 6 * plane + p;
     uchar4 ch[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) ch[c] = __ldg(reinterpret_cast<const uchar4*>(src + (size_t)c * plane));
     float4 g1, g2;
-    g1.x = grey_of(ch[0].x, ch[1].x, ch[2].x, nm); g1.y = grey_of(ch[0].y, ch[1].y, ch[2].y, nm);
-    g1.z = grey_of(ch[0].z, ch[1].z, ch[2].z, nm); g1.w = grey_of(ch[0].w, ch[1].w, ch[2].w, nm);
-    g2.x = grey_of(ch[3].x, ch[4].x, ch[5].x, nm); g2.y = grey_of(ch[3].y, ch[4].y, ch[5].y, nm);
-    g2.z = grey_of(ch[3].z, ch[4].z, ch[5].z, nm); g2.w = grey_of(ch[3].w, ch[4].w, ch[5].w, nm);
+    g1.x = grey_of(ch[0].x, ch[1].x, ch[2].x); g1.y = grey_of(ch[0].y, ch[1].y, ch[2].y);
+    g1.z = grey_of(ch[0].z, ch[1].z, ch[2].z); g1.w = grey_of(ch[0].w, ch[1].w, ch[2].w);
+    g2.x = grey_of(ch[3].x, ch[4].x, ch[5].x); g2.y = grey_of(ch[3].y, ch[4].y, ch[5].y);
+    g2.z = grey_of(ch[3].z, ch[4].z, ch[5].z); g2.w = grey_of(ch[3].w, ch[4].w, ch[5].w);
     if (grey_full) {
       float* o = grey_full + (size_t)b * 2 * plane + p;
       *reinterpret_cast<float4*>(o) = g1;
@@ -64,9 +63,7 @@ __global__ void __launch_bounds__(kThreads) pairs_u8_kernel(const uint8_t* __res
       float* o = rgb_full + (size_t)b * 6 * plane + p;
 #pragma unroll
       for (int c = 0; c < 6; ++c)
-        *reinterpret_cast<float4*>(o + (size_t)c * plane) =
-            make_float4(__fdiv_rn((float)ch[c].x, 255.f), __fdiv_rn((float)ch[c].y, 255.f), __fdiv_rn((float)ch[c].z, 255.f),
-                        __fdiv_rn((float)ch[c].w, 255.f));
+        *reinterpret_cast<float4*>(o + (size_t)c * plane) = make_float4(lut255[ch[c].x], lut255[ch[c].y], lut255[ch[c].z], lut255[ch[c].w]);
     }
     if (grey_patch) {   // img[y0 : y0 + ph, x0 : x0 + pw] of the grey images (random_crop_tt)
       const int x0 = __ldg(start + 2 * b), y0 = __ldg(start + 2 * b + 1);
@@ -97,27 +94,44 @@ __device__ __forceinline__ void src_index(int dst, int in_size, float scale, boo
   l0 = 1.f - l1;
 }
 
-// out[b, c, y, x] = rate_c * bilinear(in[b, c]), c = 0: horizontal flow (rate_x), c = 1: vertical flow (rate_y)
+// out[b, c, y, x] = rate_c * bilinear(in[b, c]), c = 0: horizontal flow (rate_x), c = 1: vertical flow (rate_y).
+// V output pixels of one row per thread (V = 4 when wo % 4 == 0: 128-bit stores, the row indices shared).
+template <int V>
 __global__ void __launch_bounds__(kThreads) flow_upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                                      int hi, int wi, int ho, int wo, float sy, float sx,
                                                                      float rate_x, float rate_y, int align) {
-  const long long plane = (long long)ho * wo, total = plane * B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane);
-    const long long p = i - (long long)b * plane;
-    const int y = (int)(p / wo), x = (int)(p - (long long)y * wo);
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
+  const long long plane = (long long)ho * wo;
+  const unsigned groups = (unsigned)(plane / V);
+  DMH_PLANE_LOOP(b, q, B, groups) {
+    const unsigned p = q * V;
+    const int y = (int)(p / (unsigned)wo), x0 = (int)(p - (unsigned)y * (unsigned)wo);
+    int y0, y1;
+    float ly0, ly1;
     src_index(y, hi, sy, align != 0, y0, y1, ly0, ly1);
-    src_index(x, wi, sx, align != 0, x0, x1, lx0, lx1);
+    float o0[V], o1[V];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const float* s = in + ((size_t)b * 2 + c) * hi * wi;
-      const float r = c ? rate_y : rate_x;
-      // the in-place `inputs[:, c] *= rate` of the reference happens before the interpolation
-      const float a = mul_rn(__ldg(s + (size_t)y0 * wi + x0), r), bq = mul_rn(__ldg(s + (size_t)y0 * wi + x1), r);
-      const float cq = mul_rn(__ldg(s + (size_t)y1 * wi + x0), r), d = mul_rn(__ldg(s + (size_t)y1 * wi + x1), r);
-      out[((size_t)b * 2 + c) * plane + p] = ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);
+    for (int v = 0; v < V; ++v) {
+      int xa, xb;
+      float lx0, lx1;
+      src_index(x0 + v, wi, sx, align != 0, xa, xb, lx0, lx1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float* s = in + ((size_t)b * 2 + c) * hi * wi;
+        const float r = c ? rate_y : rate_x;
+        // the in-place `inputs[:, c] *= rate` of the reference happens before the interpolation
+        const float a = mul_rn(__ldg(s + (size_t)y0 * wi + xa), r), bq = mul_rn(__ldg(s + (size_t)y0 * wi + xb), r);
+        const float cq = mul_rn(__ldg(s + (size_t)y1 * wi + xa), r), d = mul_rn(__ldg(s + (size_t)y1 * wi + xb), r);
+        const float val = ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);
+        if (c) o1[v] = val; else o0[v] = val;
+      }
+    }
+    float* o = out + ((size_t)b * 2) * plane + p;
+    if (V == 4) {
+      *reinterpret_cast<float4*>(o) = make_float4(o0[0], o0[1], o0[V - 2], o0[V - 1]);
+      *reinterpret_cast<float4*>(o + plane) = make_float4(o1[0], o1[1], o1[V - 2], o1[V - 1]);
+    } else {
+      o[0] = o0[0];
+      o[plane] = o1[0];
     }
   }
 }
@@ -128,12 +142,10 @@ __global__ void __launch_bounds__(kThreads) flow_upsample_fwd_kernel(const float
 __global__ void __launch_bounds__(kThreads) flow_upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int B,
                                                                      int hi, int wi, int ho, int wo, float sy, float sx,
                                                                      float rate_x, float rate_y, int align) {
-  const long long plane_i = (long long)hi * wi, total = plane_i * B;
+  const long long plane_i = (long long)hi * wi;
   const long long plane_o = (long long)ho * wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / plane_i);
-    const long long p = i - (long long)b * plane_i;
-    const int yi = (int)(p / wi), xi = (int)(p - (long long)yi * wi);
+  DMH_PLANE_LOOP(b, p, B, plane_i) {
+    const int yi = (int)(p / (unsigned)wi), xi = (int)(p - (unsigned)yi * (unsigned)wi);
     // candidate output range: the outputs whose source coordinate lies in (yi - 1, yi + 1), two pixels of slack, the
     // clamped ends widened to the border; every candidate is verified through src_index itself
     const float isy = (sy > 0.f) ? 1.f / sy : (float)ho, isx = (sx > 0.f) ? 1.f / sx : (float)wo;
@@ -181,7 +193,7 @@ extern "C" int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, floa
                                     void* stream) {
   DMH_REQUIRE(img12 && mean3 && std3, "pairs_u8_to_gray: null pointer");
   DMH_REQUIRE(gray_full || gray_patch || rgb_full, "pairs_u8_to_gray: no output requested");
-  DMH_REQUIRE(B > 0 && H > 0 && W > 0, "pairs_u8_to_gray: non-positive size");
+  DMH_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < 2147483647LL, "pairs_u8_to_gray: bad size");
   DMH_REQUIRE((W & 3) == 0, "pairs_u8_to_gray: W must be a multiple of 4 (got %d)", W);
   DMH_REQUIRE(!gray_patch || (start && patch_h > 0 && patch_w > 0), "pairs_u8_to_gray: a patch needs start (B,2) and a size");
   dmh::PairNorm nm;
@@ -190,8 +202,7 @@ extern "C" int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, floa
     nm.std[c] = std3[c];
     DMH_REQUIRE(std3[c] != 0.0, "pairs_u8_to_gray: std[%d] is zero", c);
   }
-  const long long total = (long long)B * H * W / 4;
-  dmh::pairs_u8_kernel<<<dmh::grid_for(total), dmh::kThreads, 0, dmh::as_stream(stream)>>>(img12, start, gray_full, gray_patch,
+  dmh::pairs_u8_kernel<<<dmh::plane_grid((long long)H * W / 4, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(img12, start, gray_full, gray_patch,
                                                                                         rgb_full, nm, B, H, W, patch_h, patch_w);
   return dmh::launched("pairs_u8_kernel");
 }
@@ -203,8 +214,12 @@ extern "C" int dmh_flow_upsample(const float* flow, float* out, int B, int hi, i
   const bool al = align_corners != 0;
   // Python float division w / w_ is fp64; the in-place multiply of an fp32 tensor rounds the scalar to fp32 first
   const float rx = if_rate ? (float)((double)wo / (double)wi) : 1.f, ry = if_rate ? (float)((double)ho / (double)hi) : 1.f;
-  dmh::flow_upsample_fwd_kernel<<<dmh::grid_for((long long)B * ho * wo), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
-      flow, out, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
+  if ((wo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    dmh::flow_upsample_fwd_kernel<4><<<dmh::plane_grid((long long)ho * wo / 4, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
+        flow, out, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
+  else
+    dmh::flow_upsample_fwd_kernel<1><<<dmh::plane_grid((long long)ho * wo, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
+        flow, out, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
   return dmh::launched("flow_upsample_fwd_kernel");
 }
 
@@ -214,7 +229,7 @@ extern "C" int dmh_flow_upsample_backward(const float* grad_out, float* grad_flo
   DMH_REQUIRE(B > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0, "flow_upsample_backward: non-positive size");
   const bool al = align_corners != 0;
   const float rx = if_rate ? (float)((double)wo / (double)wi) : 1.f, ry = if_rate ? (float)((double)ho / (double)hi) : 1.f;
-  dmh::flow_upsample_bwd_kernel<<<dmh::grid_for((long long)B * hi * wi), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
+  dmh::flow_upsample_bwd_kernel<<<dmh::plane_grid((long long)hi * wi, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(
       grad_out, grad_flow, B, hi, wi, ho, wo, dmh::scale_of(hi, ho, al), dmh::scale_of(wi, wo, al), rx, ry, al ? 1 : 0);
   return dmh::launched("flow_upsample_bwd_kernel");
 }

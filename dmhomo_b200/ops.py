@@ -735,9 +735,13 @@ def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEA
         if start is None:
             raise ValueError("pairs_u8_to_gray: a patch needs start (B,2)")
         ph, pw = int(patch_size[0]), int(patch_size[1])
+        if not (torch.is_tensor(start) and start.is_cuda):
+            # host-side crop origins are validated (no device round trip); device-resident ones are trusted - the
+            # kernel only ever writes patch pixels that exist, a window leaving the image leaves them unwritten
+            sh = torch.as_tensor(start).reshape(B, 2)
+            if bool(((sh[:, 0] < 0) | (sh[:, 0] + pw > W) | (sh[:, 1] < 0) | (sh[:, 1] + ph > H)).any()):
+                raise ValueError("pairs_u8_to_gray: crop window outside the image")
         st = torch.as_tensor(start, device=dev).to(torch.int32).reshape(B, 2).contiguous()
-        if bool(((st[:, 0] < 0) | (st[:, 0] + pw > W) | (st[:, 1] < 0) | (st[:, 1] + ph > H)).any()):
-            raise ValueError("pairs_u8_to_gray: crop window outside the image")
         patch = torch.empty(B, 2, ph, pw, device=dev, dtype=torch.float32)
     m3, s3 = (C.c_double * 3)(*[float(v) for v in mean]), (C.c_double * 3)(*[float(v) for v in std])
     with torch.cuda.device(dev):
