@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8, help="pairs per CPU-baseline step")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-op", action="store_true",
+                    help="cfg2 step through the one-op ops.basis_warp_loss() (forked stream branches) instead of "
+                         "basis_homography() + warp_loss(); measured equal (169.2 vs 169.0 us per step)")
     return ap.parse_args()
 
 
@@ -174,11 +177,12 @@ def run_reference(args):
 class PairStep:
     """Static buffers + the step of one workload on one GPU."""
 
-    def __init__(self, workload, dev, rank):
+    def __init__(self, workload, dev, rank, two_calls=False):
         from dmhomo_b200 import ops, synth
         from dmhomo_b200.compat import hem_utils
 
         self.ops = ops
+        self.two_calls = two_calls   # cfg2 through basis_homography() + warp_loss() instead of basis_warp_loss()
         wl = WORKLOADS[workload]
         self.wl, self.workload, self.dev = wl, workload, dev
         B, C, h, w = wl["B"], wl["C"], wl["h"], wl["w"]
@@ -204,6 +208,14 @@ class PairStep:
         ops = self.ops
         img1, img2, *par = self.sets[k]
         B, h, w = self.B, self.h, self.w
+        if self.workload == "cfg2" and not self.two_calls:
+            # the whole step as one op: weights -> H || workspace zeroing, fused warp, loss finish || adjoint DLT
+            ops.warp_timing_events = ev
+            loss = ops.basis_warp_loss(self.basis, img1, img2, par[0], par[1])
+            self.kernel_name = ops.last_warp_kernel
+            ops.warp_timing_events = None
+            loss.backward()
+            return loss
         if self.workload == "cfg2":
             # 8 basis weights -> corner offsets -> DLT, both directions, one launch
             Hf, Hb = ops.basis_homography(self.basis, h, w, par[0], par[1])
@@ -242,7 +254,7 @@ def run_ours(args):
         dist_step = True
 
     wl = WORKLOADS[args.workload]
-    st = PairStep(args.workload, dev, rank)
+    st = PairStep(args.workload, dev, rank, two_calls=not args.one_op)
     K, W = args.steps, max(args.warmup, 3)
     stream = torch.cuda.Stream(dev)
 
@@ -469,7 +481,8 @@ def run_ours(args):
             "config": {"workload": wl["desc"], "per_gpu_batch": st.B, "global_batch": st.B * world,
                        "parallelism": f"batch-sharded x{world}", "param": wl["param"],
                        "l2": f"{N_SETS} rotating input sets ({N_SETS * 2 * st.B * st.C * st.h * st.w * 4 / 1e6:.0f} MB) > 126 MB L2",
-                       "launch": "CUDA graph replay" if use_graph else "eager", "loss": final_loss},
+                       "launch": "CUDA graph replay" if use_graph else "eager", "loss": final_loss,
+                       "api": ("ops.basis_warp_loss" if (args.workload == "cfg2" and args.one_op) else "ops.basis_homography + ops.warp_loss" if args.workload == "cfg2" else "ops.dlt4 + ops.warp_loss")},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": Ke,
                     "pipeline": "copy of step i+1 on a second stream overlaps step i; loss read back and synchronised every step"},

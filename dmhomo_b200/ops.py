@@ -574,6 +574,125 @@ def warp_loss(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DI
 
 
 # ----------------------------------------------------------------------------------------------
+# the whole unsupervised step of cfg 2 in one op: 8 basis weights -> H -> bidirectional warp loss + all gradients
+# ----------------------------------------------------------------------------------------------
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One auxiliary stream per device for the short fork / join branches of basis_warp_loss."""
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(dev)
+    return _side_streams[key]
+
+
+class _BasisWarpLoss(torch.autograd.Function):
+    """basis_homography + warp_loss(two directions, fused gradients) + the adjoint DLT, with the independent
+    pieces on forked branches (they become parallel nodes when the step is captured into a CUDA graph):
+
+        zero the gradient workspace  ||  weights -> corner offsets -> DLT -> Hf, Hb
+                            fused warp kernel (loss sums + dL/dimg + dL/dH)
+        loss finish                  ||  dL/dH -> adjoint DLT -> dL/dweights
+
+    The backward only rescales the stored gradients by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, basis, img1, img2, w_f, w_b, weight):
+        dev = _cuda(basis, img1, img2, w_f, w_b)
+        bc, i1, i2 = _f32(basis), _f32(img1), _f32(img2)
+        wf, wb = _f32(w_f).reshape(-1, 8), _f32(w_b).reshape(-1, 8)
+        B, Cc, h, w = i1.shape
+        if i2.shape != i1.shape or wf.shape[0] != B or wb.shape[0] != B or bc.numel() != 16 * h * w:
+            raise ValueError("basis_warp_loss: img1/img2 (B,C,h,w), weights (B,8), basis (8,2,h,w) shapes disagree")
+        needs = ctx.needs_input_grad
+        any_grad = bool(needs[1] or needs[2] or needs[3] or needs[4])
+        n_img, acc_floats = i1.numel(), 4 * B
+        # workspace: [loss accumulators (fp64, 2 x B) | dL/dimg1 | dL/dimg2 | dL/dHf | dL/dHb | dL/dwf | dL/dwb]
+        off_g1, off_g2 = acc_floats, acc_floats + n_img
+        off_hf = off_g2 + n_img
+        off_hb, off_wf, off_wb = off_hf + 9 * B, off_hf + 18 * B, off_hf + 26 * B
+        total = off_hf + 34 * B if any_grad else acc_floats
+        ws = torch.empty(total, device=dev, dtype=torch.float32)
+        Hf = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+        Hb = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        lib = L.lib()
+        scale = float(weight) / float(B * Cc * h * w)
+        with torch.cuda.device(dev):
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(cur)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                ws.zero_()
+                join.record(side)
+            wp = (C.c_void_p * 2)(wf.data_ptr(), wb.data_ptr())
+            hp = (C.c_void_p * 2)(Hf.data_ptr(), Hb.data_ptr())
+            L.check(lib.dmh_basis_homography_forward(_p(bc), wp, hp, 2, B, h, w, _stream(dev)), "basis_homography_forward")
+            cur.wait_event(join)
+            acc = ws[:acc_floats].view(torch.float64)
+            g1 = ws[off_g1:off_g1 + n_img] if any_grad else None
+            g2 = ws[off_g2:off_g2 + n_img] if any_grad else None
+            ghf = ws[off_hf:off_hf + 9 * B] if any_grad else None
+            ghb = ws[off_hb:off_hb + 9 * B] if any_grad else None
+            common = dict(use_border_mask=True, loss_form=LOSS_MASKED_DIFF, grad_loss_scale=scale, compute_grads=any_grad)
+            descs = [_desc(S1, PARAM_HOMOGRAPHY, i2, Hf, h, w, target=i1, loss_acc=acc[:B], grad_src=g2, grad_target=g1,
+                           grad_param=ghf, **common),
+                     _desc(S1, PARAM_HOMOGRAPHY, i1, Hb, h, w, target=i2, loss_acc=acc[B:], grad_src=g1, grad_target=g2,
+                           grad_param=ghb, **common)]
+            _run_warp(descs, dev)
+            fork2, join2 = torch.cuda.Event(), torch.cuda.Event()
+            fork2.record(cur)
+            side.wait_event(fork2)
+            with torch.cuda.stream(side):
+                acc_ptrs = (C.c_void_p * 2)(acc[:B].data_ptr(), acc[B:].data_ptr())
+                sw_ptrs = (C.c_void_p * 2)(None, None)
+                L.check(lib.dmh_loss_finish(acc_ptrs, sw_ptrs, 2, B, scale, _p(loss), C.c_void_p(side.cuda_stream)), "loss_finish")
+                join2.record(side)
+            if any_grad:
+                gp = (C.c_void_p * 2)(ghf.data_ptr(), ghb.data_ptr())
+                gwp = (C.c_void_p * 2)(ws[off_wf:off_wf + 8 * B].data_ptr(), ws[off_wb:off_wb + 8 * B].data_ptr())
+                L.check(lib.dmh_basis_homography_backward(_p(bc), hp, gp, gwp, 2, B, h, w, _stream(dev)),
+                        "basis_homography_backward")
+            cur.wait_event(join2)
+        ctx.cfg = (any_grad, acc_floats, n_img, off_g1, off_g2, off_wf, off_wb, B, i1.shape, w_f.shape, w_b.shape)
+        ctx.save_for_backward(ws)
+        ctx.mark_non_differentiable(Hf, Hb)
+        return loss, Hf, Hb
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        any_grad, acc_floats, n_img, off_g1, off_g2, off_wf, off_wb, B, ishape, wfs, wbs = ctx.cfg
+        if not any_grad:
+            return (None,) * 6
+        (ws,) = ctx.saved_tensors
+        g = _f32(g)
+        dev = g.device
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_scale_inplace(ws[acc_floats:].data_ptr(), ws.numel() - acc_floats, _p(g), _stream(dev)),
+                    "scale_inplace")
+        needs = ctx.needs_input_grad
+        return (None,
+                ws[off_g1:off_g1 + n_img].view(ishape) if needs[1] else None,
+                ws[off_g2:off_g2 + n_img].view(ishape) if needs[2] else None,
+                ws[off_wf:off_wf + 8 * B].view(wfs) if needs[3] else None,
+                ws[off_wb:off_wb + 8 * B].view(wbs) if needs[4] else None,
+                None)
+
+
+def basis_warp_loss(basis, img1, img2, w_f, w_b, weight=1.0, return_homographies=False):
+    """The unsupervised HEM term on the DLT variant of cfg 2 as ONE op:
+        Hf, Hb = basis_homography(basis, h, w, w_f, w_b)
+        loss   = weight * (L1(m_f*img1, m_f*warp(img2, Hf)) + L1(m_b*img2, m_b*warp(img1, Hb)))     (losses.py:142-146)
+    with the gradients to both images and both weight sets computed in the same pass.  Numerically identical to
+    warp_loss([WarpTerm(img2, img1, Hf), WarpTerm(img1, img2, Hb)]) after basis_homography - the same kernels - but the
+    independent launches (workspace zeroing / weights -> H; loss finish / adjoint DLT) sit on forked stream branches."""
+    loss, Hf, Hb = _BasisWarpLoss.apply(basis, img1, img2, w_f, w_b, float(weight))
+    return (loss, Hf, Hb) if return_homographies else loss
+
+
+# ----------------------------------------------------------------------------------------------
 # masks, plain L1
 # ----------------------------------------------------------------------------------------------
 def border_mask(flow, as_float=False):

@@ -593,3 +593,57 @@ def test_no_cpu_fallback():
         ops.warp(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4))
     with pytest.raises(RuntimeError):
         ops.dlt4(torch.zeros(1, 4, 2), torch.zeros(1, 4, 2))
+
+
+def test_basis_warp_loss_one_op_matches_composition_and_graph_replay():
+    """ops.basis_warp_loss (one op, forked stream branches) == basis_homography + warp_loss (same kernels): loss,
+    homographies and every gradient; also against the oracle, and replayed from a CUDA graph (the form bench.py runs)."""
+    B, h, w = 3, 64, 96
+    gen = synth.generator()
+    img1, img2 = synth.smooth_images(B, 1, h, w, gen), synth.smooth_images(B, 1, h, w, gen)
+    basis = hem_utils.gen_basis(h, w)
+    wf, wb = synth.basis_weights(B, gen, 2.0), synth.basis_weights(B, gen, 2.0)
+    bd = basis.to(DEV)
+
+    def leaves():
+        return [t.clone().to(DEV).requires_grad_(True) for t in (img1, img2, wf, wb)]
+
+    a = leaves()
+    Hf, Hb = ops.basis_homography(bd, h, w, a[2], a[3])
+    la = ops.warp_loss([ops.WarpTerm(a[1], a[0], Hf), ops.WarpTerm(a[0], a[1], Hb)], kind=ops.PARAM_HOMOGRAPHY)
+    la.backward()
+    b = leaves()
+    lb, Hf2, Hb2 = ops.basis_warp_loss(bd, b[0], b[1], b[2], b[3], return_homographies=True)
+    lb.backward()
+    assert torch.equal(Hf2, Hf.detach()) and torch.equal(Hb2, Hb.detach())
+    assert abs(la.item() - lb.item()) < 1e-7
+    for x, y in zip(a, b):
+        assert (x.grad - y.grad).abs().max().item() <= 1e-6 * max(1.0, x.grad.abs().max().item())
+
+    lc = [t.clone().requires_grad_(True) for t in (img1, img2, wf, wb)]
+    ref = port.pipeline_basis(lc[0], lc[1], basis.reshape(1, 8, -1), lc[2], lc[3], variant="dlt", backward=True)
+    assert abs(lb.item() - ref["loss"].item()) < 1e-4
+    for x, y in zip(b[:2], lc[:2]):
+        assert (x.grad.cpu() - y.grad).abs().max().item() < 1e-4
+
+    # CUDA-graph capture of the whole step (forked branches become parallel nodes), replayed twice
+    c = leaves()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            for t in c:
+                t.grad = None
+            ops.basis_warp_loss(bd, c[0], c[1], c[2], c[3]).backward()
+        stream.synchronize()
+        for t in c:
+            t.grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            lg = ops.basis_warp_loss(bd, c[0], c[1], c[2], c[3])
+            lg.backward()
+        for _ in range(2):
+            g.replay()
+        stream.synchronize()
+    assert abs(lg.item() - lb.item()) < 1e-7
+    for x, y in zip(c, b):
+        assert (x.grad - y.grad).abs().max().item() <= 1e-6 * max(1.0, y.grad.abs().max().item())
