@@ -647,3 +647,29 @@ def test_basis_warp_loss_one_op_matches_composition_and_graph_replay():
     assert abs(lg.item() - lb.item()) < 1e-7
     for x, y in zip(c, b):
         assert (x.grad - y.grad).abs().max().item() <= 1e-6 * max(1.0, y.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("h,w", [(5, 7), (8, 12), (3, 4), (17, 33), (2, 64)])
+def test_elementwise_kernels_scalar_and_vector_paths(h, w):
+    """The one-pass kernels take four pixels per thread with 128-bit accesses when w % 4 == 0 and one otherwise;
+    both paths, on tiny and ragged planes, bit-exact against the oracle (get_flow, the fp64 flows / mappings in both
+    layouts, the M1 mask as bool and as float)."""
+    B = 3
+    src = port.corner_points(B, max(h, 4), max(w, 4))
+    H = port.dlt4(src, src + synth.corner_offsets(B, 1.5, g(91)))
+    for start in (0, 2):
+        assert torch.equal(ops.homography_to_flow(H.to(DEV), h, w, start=start).cpu(), port.homography_to_flow(H, h, w, start=start)[0])
+    H64 = H.double().numpy()
+    f64 = ops.homography_to_flow_f64(torch.from_numpy(H64).to(DEV), h, w).cpu()                      # (B,h,w,2), eps 1e-6
+    fcf = ops.homography_to_flow_f64(torch.from_numpy(H64).to(DEV), h, w, channels_last=False).cpu()
+    gt = ops.homography_to_flow_f64(torch.from_numpy(H64).to(DEV), h, w, eps=1e-8, channels_last=False, as_mapping=2).cpu()
+    mp = ops.homography_to_flow_f64(torch.from_numpy(H64).to(DEV), h, w, eps=1e-8, channels_last=False, as_mapping=True).cpu()
+    for b in range(B):
+        ref = torch.from_numpy(port.homo_to_flow_np(H64[b], h, w))
+        assert torch.equal(f64[b], ref) and torch.equal(fcf[b], ref.permute(2, 0, 1))
+        assert torch.equal(gt[b], port.homo_convert_to_flow(H64[b], (h, w))[0])
+        mx, my = port.homography_to_mapping_np((h, w), H64[b])
+        assert torch.equal(mp[b, 0], torch.from_numpy(mx)) and torch.equal(mp[b, 1], torch.from_numpy(my))
+    flow = torch.randn(B, 2, h, w, generator=g(92)) * (w / 2)
+    assert torch.equal(ops.border_mask(flow.to(DEV)).cpu(), port.correspondence_mask(flow))
+    assert torch.equal(ops.border_mask(flow.to(DEV), as_float=True).cpu(), port.border_mask(flow).reshape(B, h, w))
