@@ -127,3 +127,25 @@ def test_tile_flags_imply_what_the_fast_bodies_assume(kind, h, w):
         assert n_int > 0.3 * n_tiles and n_full > 0.9 * n_tiles      # the fast bodies carry the typical workload
     if kind == "horizon":
         assert n_int < n_tiles                                        # and are refused where they must be
+
+
+def test_interior_weight_identities_are_exact():
+    """The interior body replaces fl(x1 - cx) by fl(1 - fl(cx - x0)) (x1 = x0 + 1, no clamp) and takes floor(cx) from the
+    mantissa of fl_down(cx + 2^23).  Both are claimed bit-exact for 0 <= cx < 2^22: ax0 = cx - floor(cx) is exact
+    (Sterbenz), so 1 - ax0 and x1 - cx are the same real number before the single rounding."""
+    rs = np.random.default_rng(5)
+    cx = np.concatenate([
+        rs.uniform(0, 4096, 2_000_000), rs.uniform(0, 2, 500_000), rs.uniform(0, 1e-3, 200_000),
+        np.arange(0, 2048, dtype=np.float64), np.nextafter(np.arange(1, 2048, dtype=np.float32), np.float32(0)).astype(np.float64),
+        np.nextafter(np.arange(0, 2048, dtype=np.float32), np.float32(1e9)).astype(np.float64),
+        rs.uniform(4096, 2 ** 22 - 1, 500_000)]).astype(f32)
+    x0 = np.floor(cx)                                   # exact in fp32
+    ax0 = (cx - x0).astype(f32)
+    assert np.array_equal(ax0.astype(np.float64), cx.astype(np.float64) - x0.astype(np.float64)), "cx - floor(cx) must be exact"
+    ref = ((x0 + f32(1)).astype(f32) - cx).astype(f32)  # the reference: x1f - cx with x1 = x0 + 1
+    new = (f32(1) - ax0).astype(f32)
+    assert np.array_equal(ref, new)
+    # round-down add of 2^23: emulated in fp64 (exact sum) + floor to the fp32 grid of [2^23, 2^24), which is the integers
+    magic = np.floor(cx.astype(np.float64) + 8388608.0)
+    assert np.array_equal(magic - 8388608.0, x0.astype(np.float64))
+    assert np.array_equal((magic.astype(np.int64) & 0x7FFFFF), x0.astype(np.int64))   # mantissa bits = the integer
