@@ -167,6 +167,34 @@ def main():
 
 
 
+    # ---- cfg 2 chained through the reference's own functions, with gradients -----------
+    # gen_basis -> (basis * w).sum(1) -> the flow at the four corners as 4-pt offsets -> DLT -> get_flow ->
+    # get_warp_flow (both directions) -> create_border_mask -> LossL1, backward to both images and both weight sets
+    Bc, hc, wc = 3, 64, 96
+    basis_c = U.gen_basis(hc, wc).reshape(1, 8, -1)
+    c1 = torch.rand(Bc, 1, hc, wc, generator=g(71)).requires_grad_(True)
+    c2 = torch.rand(Bc, 1, hc, wc, generator=g(72)).requires_grad_(True)
+    wfc = ((torch.rand(Bc, 8, 1, generator=g(73)) * 2 - 1) * 2.0).requires_grad_(True)
+    wbc = ((torch.rand(Bc, 8, 1, generator=g(74)) * 2 - 1) * 2.0).requires_grad_(True)
+    sc = corners(Bc, hc, wc)
+
+    def corner_offsets(wt):
+        fl = (basis_c * wt).sum(1).reshape(Bc, 2, hc, wc)           # net.py:808-809
+        pts = [fl[:, :, 0, 0], fl[:, :, 0, wc - 1], fl[:, :, hc - 1, 0], fl[:, :, hc - 1, wc - 1]]
+        return torch.stack(pts, 1)                                  # (B,4,2) in the corner order of `corners`
+
+    Hfc, Hbc = U.DLT(Bc)(sc, sc + corner_offsets(wfc)), U.DLT(Bc)(sc, sc + corner_offsets(wbc))
+    gc = U.get_grid(Bc, hc, wc, 0)
+    ffc, _ = U.get_flow(Hfc.view(Bc, 1, 3, 3), gc, hc, wc, 1)
+    fbc, _ = U.get_flow(Hbc.view(Bc, 1, 3, 3), gc, hc, wc, 1)
+    w2c, w1c = U.get_warp_flow(c2, ffc), U.get_warp_flow(c1, fbc)
+    mfc, mbc = F.create_border_mask(ffc).unsqueeze(1), F.create_border_mask(fbc).unsqueeze(1)
+    l1c = L.LossL1(reduction="mean")
+    lossc = l1c(mfc * c1, mfc * w2c) + l1c(mbc * c2, mbc * w1c)
+    lossc.backward()
+    save("pipeline_basis", img1=c1, img2=c2, w_f=wfc, w_b=wbc, Hf=Hfc, Hb=Hbc, flow_f=ffc, flow_b=fbc, w2=w2c, w1=w1c,
+         loss=lossc, g_img1=c1.grad, g_img2=c2.grad, g_wf=wfc.grad, g_wb=wbc.grad, hw=np.array([hc, wc]))
+
     # ---- section 8f rows 2-4: uint8 pair format, loader GT flow, flow upsample ------------------------
     import types
     DL = r.data_loader

@@ -163,3 +163,19 @@ def test_upsample_golden():
     for name, (rate,) in {"x4_rate": (True,), "odd_rate": (True,), "down": (False,), "x2_norate": (False,)}.items():
         tgt = torch.zeros(1, 1, *d[name].shape[-2:])
         assert torch.equal(port.upsample2d_flow_as(fl, tgt, if_rate=rate), d[name]), name
+
+
+def test_pipeline_basis_golden():
+    """cfg 2 (the headline configuration) chained through the reference's own functions, gradients included."""
+    d = load("pipeline_basis")
+    h, w = [int(v) for v in d["hw"]]
+    leaves = [d[k].clone().requires_grad_(True) for k in ("img1", "img2", "w_f", "w_b")]
+    out = port.pipeline_basis(leaves[0], leaves[1], port.gen_basis(h, w).reshape(1, 8, -1), leaves[2], leaves[3],
+                              variant="dlt", backward=True)
+    assert rel_fro(out["Hf"].detach(), d["Hf"]) < 1e-6 and rel_fro(out["Hb"].detach(), d["Hb"]) < 1e-6
+    assert (out["flow_f"].detach() - d["flow_f"]).abs().max().item() < 1e-4
+    assert (out["w2"].detach() - d["w2"]).abs().max().item() < 1e-4 and (out["w1"].detach() - d["w1"]).abs().max().item() < 1e-4
+    assert abs(out["loss"].item() - d["loss"].item()) < 1e-6
+    assert (leaves[0].grad - d["g_img1"]).abs().max().item() < 1e-6
+    assert (leaves[1].grad - d["g_img2"]).abs().max().item() < 1e-6
+    assert rel_fro(leaves[2].grad, d["g_wf"]) < 1e-3 and rel_fro(leaves[3].grad, d["g_wb"]) < 1e-3
