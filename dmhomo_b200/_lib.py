@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DMH_LIB: development knob, an alternative build of the same library (tools/build_variants.sh A/B runs)
 LIB_PATH = os.environ.get("DMH_LIB") or os.path.join(_HERE, "libdmhomo.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/dmhomo.h
 S1, S1B, S2_ZEROS, S3_BORDER = 0, 1, 2, 3
@@ -72,6 +72,8 @@ SIGNATURES = {
     "dmh_last_error_string": [],
     "dmh_launch_count": [],
     "dmh_last_kernel_name": [],
+    "dmh_set_tuning": [C.c_char_p, _i],
+    "dmh_get_tuning": [C.c_char_p, C.POINTER(_i)],
     "dmh_warp_forward": [C.POINTER(WarpDesc), _i, _fp],
     "dmh_warp_backward": [C.POINTER(WarpDesc), _i, _fp],
     "dmh_loss_finish": [C.POINTER(_fp), C.POINTER(_fp), _i, _i, _f, _fp, _fp],
@@ -130,6 +132,11 @@ def lib():
         if l.dmh_version() != ABI_VERSION:
             raise DmhError(f"dmhomo_b200: ABI version {l.dmh_version()} != expected {ABI_VERSION}")
         _lib = l
+        # DMH_TUNING="key=value,...": development knob of this binding (the library itself reads no environment)
+        for kv in filter(None, os.environ.get("DMH_TUNING", "").split(",")):
+            k, _, v = kv.partition("=")
+            if l.dmh_set_tuning(k.strip().encode(), int(v)) != 0:
+                raise DmhError(f"dmhomo_b200: bad DMH_TUNING entry {kv!r}")
     return _lib
 
 
@@ -146,3 +153,15 @@ def launch_count():
 def last_kernel_name():
     n = lib().dmh_last_kernel_name()
     return n.decode() if n else ""
+
+
+def set_tuning(**knobs):
+    """dmh_set_tuning(): development knobs of the library (include/dmhomo.h), e.g. set_tuning(tile=0)."""
+    for k, v in knobs.items():
+        check(lib().dmh_set_tuning(k.encode(), int(v)), f"set_tuning({k})")
+
+
+def get_tuning(key):
+    v = C.c_int(0)
+    check(lib().dmh_get_tuning(key.encode(), C.byref(v)), f"get_tuning({key})")
+    return v.value

@@ -39,6 +39,14 @@ inline int launched(const char* what) {
     if (!(cond)) return ::dmh::fail(DMH_EINVAL, __VA_ARGS__); \
   } while (0)
 
+// Development knobs (dmh_set_tuning): plain ints read at launch time.  Defaults are the measured best; none of them
+// changes a result.  Not meant to be raced against launches from other threads.
+struct Tuning {
+  int tile = 2;           // 0: scalar kernels only; 1: TMA tile kernel for the dense C = 1 launches; 2: also C = 3
+  int tile_interior = 3;  // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body
+};
+Tuning& tuning();
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200

@@ -18,8 +18,6 @@
 #include "dmh_sampler.cuh"
 #include "dmh_warp_fast.h"
 
-#include <cstdlib>
-
 namespace dmh {
 
 namespace {
@@ -35,8 +33,6 @@ enum { PASS_FWD = 0, PASS_BWD = 1, PASS_FUSED = 2 };
 constexpr int kTuneDense = 0 | 3 << 4 | 4 << 8;
 constexpr int kTuneGeneral = 0 | 3 << 4 | 2 << 8;
 constexpr int kTuneDenseC3 = 0 | 3 << 4 | 3 << 8;   // cfg4 sweep: 80 registers, 3 CTAs/SM
-constexpr int kTileDefault = 1;    // 1 = dense S1 homography forward / fused launches go to dmh_warp_tile.cu
-constexpr int kStageDefault = 0;   // 0 off, 3 / 4 = staged kernel with a 3 / 4 CTAs-per-SM register budget
 
 // Explicit global-space accesses (the pinned bases below are opaque to the compiler, which would
 // otherwise fall back to generic-address atomics): ld.global.nc, st.global, red.global.add.
@@ -62,40 +58,6 @@ __device__ __forceinline__ T* pin(T* p) {
   asm volatile("" : "+l"(p));
   return p;
 }
-// ---- shared-memory staging (TUNE bit 12): bulk async copies (cp.async.bulk -> SASS UBLKCP) of the
-// source window and the target tile of a CTA, completion through an mbarrier ---------------------
-constexpr int kWinCap = 9216;      // floats per channel of the staged source window (36 KB)
-constexpr int kWinPitchMax = 160;  // floats per staged row
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ float lds_f(unsigned addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float rcp_fast(float x) {
   float r;
@@ -114,7 +76,6 @@ template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS, int PROFILE, int T
 __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const __grid_constant__ FastArgs a) {
   constexpr bool kPipe = (TUNE & 1) != 0;
   constexpr int kPF = (TUNE >> 4) & 15;
-  constexpr bool kStage = ((TUNE >> 12) & 1) != 0;   // S1 + one homography per sample + dense profile only
   constexpr bool kGrad = (PASS != PASS_FWD);
   constexpr bool kOut = (PASS != PASS_BWD);
   constexpr bool kLoss = (LOSS != DMH_LOSS_NONE);
@@ -169,62 +130,6 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
     h0x = mul_rn(hm[0], gx);
     h3x = mul_rn(hm[3], gx);
     h6x = mul_rn(hm[6], gx);
-  }
-
-  // ---- staging: source window = bounding box of the tile's image under H (a projective map with
-  // T > 0 on the tile sends it to a convex quad: the four corners bound every pixel), one pixel of
-  // margin for rounding, +1 for the x1 / y1 taps, clipped to the source, columns aligned to 16 bytes.
-  // Taps that fall outside what was staged (degenerate H, window larger than the capacity) take the
-  // global path, so the result never depends on the window.
-  extern __shared__ __align__(16) unsigned char stage_raw[];
-  int wx0 = 0, wy0 = 0, wpitch = 0, wrows = 0;
-  const int tx0 = txi * TW, ty0 = tyi * TH;
-  unsigned win_s = 0, tgt_s = 0;
-  if (kStage) {
-    const int tx1 = min(tx0 + TW, w) - 1, ty1 = min(ty0 + TH, h) - 1;
-    float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float px = (float)((k & 1) ? tx1 : tx0) + sx, py = (float)((k & 2) ? ty1 : ty0) + sy;
-      const float T = hm[6] * px + hm[7] * py + hm[8];
-      const float rT = 1.0f / T;
-      const float ux = (hm[0] * px + hm[1] * py + hm[2]) * rT, uy = (hm[3] * px + hm[4] * py + hm[5]) * rT;
-      ok = ok && (T > 1e-4f) && (fabsf(ux) < 1.0e7f) && (fabsf(uy) < 1.0e7f);
-      mnx = fminf(mnx, ux); mxx = fmaxf(mxx, ux); mny = fminf(mny, uy); mxy = fmaxf(mxy, uy);
-    }
-    if (ok) {
-      const int x_lo = max((int)floorf(mnx) - 1, 0), x_hi = min((int)floorf(mxx) + 2, Ws - 1);
-      const int y_lo = max((int)floorf(mny) - 1, 0), y_hi = min((int)floorf(mxy) + 2, Hs - 1);
-      if (x_hi >= x_lo && y_hi >= y_lo) {
-        wx0 = x_lo & ~3;
-        wpitch = ((x_hi + 4) & ~3) - wx0;          // Ws % 4 == 0 (host check) keeps wx0 + wpitch <= Ws
-        wy0 = y_lo;
-        wrows = y_hi - y_lo + 1;
-        if (wpitch > kWinPitchMax) wrows = 0; else wrows = min(wrows, kWinCap / wpitch);
-      }
-    }
-    const unsigned bar = smem_u32(stage_raw);
-    win_s = bar + 16;
-    tgt_s = win_s + (unsigned)(CT * kWinCap * 4);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (wrp == 0) {
-      const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
-      if (lane == 0) mbar_expect_tx(bar, (unsigned)(CT * (wrows * wpitch + (kLoss ? th * tw : 0)) * 4));
-      for (int r = lane; r < CT * wrows; r += 32) {
-        const int c = r / wrows, rr = r - c * wrows;
-        bulk_g2s(win_s + (unsigned)((c * kWinCap + rr * wpitch) * 4),
-                 src + ((size_t)c * plane_s + (size_t)(wy0 + rr) * Ws + wx0), (unsigned)(wpitch * 4), bar);
-      }
-      if (kLoss) {
-        for (int r = lane; r < CT * th; r += 32) {
-          const int c = r / th, rr = r - c * th;
-          bulk_g2s(tgt_s + (unsigned)((c * TH * TW + rr * TW) * 4),
-                   tgt + ((size_t)c * plane_o + (size_t)(ty0 + rr) * w + tx0), (unsigned)(tw * 4), bar);
-        }
-      }
-    }
   }
 
   float gscale = 0.f;
@@ -305,33 +210,14 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
         prefetch_l1(src + ((unsigned)c * plane_s + ps));
       }
     }
-    bool staged = false;
-    unsigned sa_ = 0, sb_ = 0, sc_ = 0, sd_ = 0;
-    if (kStage) {
-      const int dx0 = x0 - wx0, dx1 = x1 - wx0, dy0 = y0 - wy0, dy1 = y1 - wy0;
-      staged = (dx0 >= 0) && (dx1 < wpitch) && (dy0 >= 0) && (dy1 < wrows);
-      const unsigned r0 = win_s + (unsigned)(dy0 * wpitch) * 4u, r1 = win_s + (unsigned)(dy1 * wpitch) * 4u;
-      sa_ = r0 + (unsigned)dx0 * 4u; sb_ = r1 + (unsigned)dx0 * 4u; sc_ = r0 + (unsigned)dx1 * 4u; sd_ = r1 + (unsigned)dx1 * 4u;
-    }
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
       const unsigned cs = (unsigned)c * plane_s, oo = po + (unsigned)c * plane_o;
-      if (kStage && staged) {
-        const unsigned co = (unsigned)(c * kWinCap * 4);
-        r.I[c][0] = lds_f(sa_ + co);
-        r.I[c][1] = lds_f(sb_ + co);
-        r.I[c][2] = lds_f(sc_ + co);
-        r.I[c][3] = lds_f(sd_ + co);
-      } else {
-        r.I[c][0] = ldg_f(src, cs + tp.ia);
-        r.I[c][1] = ldg_f(src, cs + tp.ib);
-        r.I[c][2] = ldg_f(src, cs + tp.ic);
-        r.I[c][3] = ldg_f(src, cs + tp.id);
-      }
-      if (kStage)
-        r.tv[c] = kLoss ? lds_f(tgt_s + (unsigned)(((c * TH + (y - ty0)) * TW + (x - tx0)) * 4)) : 0.f;
-      else
-        r.tv[c] = kLoss ? ldg_f(tgt, oo) : 0.f;
+      r.I[c][0] = ldg_f(src, cs + tp.ia);
+      r.I[c][1] = ldg_f(src, cs + tp.ib);
+      r.I[c][2] = ldg_f(src, cs + tp.ic);
+      r.I[c][3] = ldg_f(src, cs + tp.id);
+      r.tv[c] = kLoss ? ldg_f(tgt, oo) : 0.f;
       r.go[c] = (!kDense && PASS == PASS_BWD && gout) ? ldg_f(gout, oo) : 0.f;
     }
   };
@@ -432,7 +318,6 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
     }
   };
 
-  if (kStage) mbar_wait(smem_u32(stage_raw), 0);   // every thread: the staged bytes have landed
   if (col_live && y_begin < y_end) {
     if (kPipe) {
       Row r0, r1;
@@ -507,56 +392,6 @@ int launch(const FastArgs& a, int n, long long tiles, int flags, cudaStream_t st
   const bool dense = (flags & 1) != 0;
   if constexpr (kHasDense) {
     if (dense) {
-      if constexpr (PARAM == DMH_PARAM_HOMOGRAPHY && CT == 1) {
-        // staged: source window + target tile through cp.async.bulk into shared memory
-        static const int stage_mode = getenv("DMH_STAGE") ? atoi(getenv("DMH_STAGE")) : kStageDefault;
-        if ((flags & 2) && stage_mode > 0) {
-          constexpr bool kL = (LOSS != DMH_LOSS_NONE);
-          constexpr int smem = 16 + CT * kWinCap * 4 + (kL ? CT * TH * TW * 4 : 0);
-          if (stage_mode == 3) {
-            auto kern = warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (3 << 8 | 1 << 12)>;
-            static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            (void)attr;
-            kern<<<grid, NT, smem, stream>>>(a);
-          } else {
-            auto kern = warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (4 << 8 | 1 << 12)>;
-            static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            (void)attr;
-            kern<<<grid, NT, smem, stream>>>(a);
-          }
-          return launched("warp_fast_kernel(staged)");
-        }
-      }
-      if constexpr (PARAM == DMH_PARAM_HOMOGRAPHY && PASS != PASS_BWD) {
-        // persistent tiled kernel (dmh_warp_tile.cu): bulk-copy staged window / target, packed fp32
-        static const int tile_mode = getenv("DMH_TILE") ? atoi(getenv("DMH_TILE")) : kTileDefault;
-        // C = 3 stays on the scalar kernel (measured: cfg4 4.97 ms scalar vs 5.54 ms tiled); DMH_TILE=2 forces it
-        if ((flags & 4) && tile_mode > 0 && (CT == 1 || tile_mode > 1)) {
-          FastArgs at = a;
-          const int rc = warp_tile_launch(at, n, PASS, CT, stream);
-          if (rc != 1) return rc;
-        }
-      }
-      if constexpr (PASS != PASS_BWD) {
-        // Measured (profiles/r1_tune_sweeps.txt): the paired kernel executes 21 % fewer instructions but its
-        // register footprint halves the resident warps and it ends up ~3 % slower; opt-in until it is staged.
-        static const bool use_pair = getenv("DMH_PAIR") != nullptr;
-        if (use_pair) {
-          FastArgs ap = a;
-          return warp_pair_launch(ap, n, tiles, PARAM, PASS, CT, stream);
-        }
-      }
-#ifdef DMH_TUNE_BUILD
-      if (PASS == PASS_FUSED && PARAM == DMH_PARAM_HOMOGRAPHY) {
-        static const int tune = getenv("DMH_TUNE") ? atoi(getenv("DMH_TUNE")) : 0;
-        switch (tune) {
-#define DMH_T(P, F, M) case (P | F << 4 | M << 8): warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (P | F << 4 | M << 8)><<<grid, NT, 0, stream>>>(a); return launched("warp_fast_kernel");
-          DMH_T(0, 0, 3) DMH_T(0, 2, 3) DMH_T(0, 3, 3) DMH_T(0, 4, 3) DMH_T(1, 0, 3) DMH_T(1, 3, 3) DMH_T(1, 3, 2) DMH_T(0, 3, 4) DMH_T(0, 0, 4) DMH_T(0, 3, 2)
-#undef DMH_T
-          default: break;
-        }
-      }
-#endif
       warp_fast_kernel<SAMPLER, PARAM, PASS, CT, LOSS, 1, (CT == 1) ? kTuneDense : kTuneDenseC3><<<grid, NT, 0, stream>>>(a);
       return launched("warp_fast_kernel");
     }
@@ -627,14 +462,6 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
     t.grad_loss_scale = s.grad_loss_scale;
     t.use_border_mask = s.use_border_mask;
   }
-  bool stage_ok = (d0.Ws % 4 == 0) && (d0.w % 4 == 0);
-  for (int i = 0; i < n; ++i)
-    stage_ok = stage_ok && ((reinterpret_cast<uintptr_t>(d[i].src) & 15) == 0) &&
-               ((reinterpret_cast<uintptr_t>(d[i].target) & 15) == 0);
-  bool tile_ok = stage_ok && (d0.h % 2 == 0);
-  for (int i = 0; i < n; ++i)
-    tile_ok = tile_ok && ((reinterpret_cast<uintptr_t>(d[i].out) & 15) == 0) &&
-              ((reinterpret_cast<uintptr_t>(d[i].grad_target) & 15) == 0);
   if (n == 1) a.t[1] = a.t[0];
   a.B = d0.B; a.Hs = d0.Hs; a.Ws = d0.Ws; a.h = d0.h; a.w = d0.w;
   a.sx = d0.start_x; a.sy = d0.start_y;
@@ -642,13 +469,42 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
   a.tiles_y = (d0.h + TH - 1) / TH;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * d0.B;
   if (tiles > 2147483647LL) return 1;
+  // ---- the persistent TMA tile kernel takes the dense S1 homography launches (dmh_warp_tile.cu) ----
+  const int tile_mode = tuning().tile;
+  if (d0.sampler == DMH_S1 && d0.param_kind == DMH_PARAM_HOMOGRAPHY && pass != PASS_BWD && tile_mode > 0 &&
+      (d0.C == 1 || tile_mode > 1)) {
+    int mode = -1;
+    for (int i = 0; i < n; ++i) {
+      const dmh_warp_desc& s = d[i];
+      int m = 0;
+      const bool aligned = ((reinterpret_cast<uintptr_t>(s.src) | reinterpret_cast<uintptr_t>(s.target) |
+                             reinterpret_cast<uintptr_t>(s.out) | reinterpret_cast<uintptr_t>(s.grad_target)) & 15) == 0;
+      const bool l1 = loss == DMH_LOSS_MASKED_DIFF && s.target && s.loss_acc && s.use_border_mask;
+      if (!aligned || s.soft_mask || s.grad_out || (loss != DMH_LOSS_NONE && !l1)) {
+        m = 0;
+      } else if (pass == PASS_FUSED) {
+        m = (l1 && s.grad_src && s.grad_target && s.grad_param && !s.grad_soft_mask) ? 6 : 0;
+      } else if (s.out && s.valid) {
+        m = 1 | (l1 ? 2 : 0);
+      } else if (!s.out && !s.valid && l1) {
+        m = 2;
+      }
+      mode = (i == 0 || m == mode) ? m : 0;
+      if (mode == 0) break;
+    }
+    if (mode > 0) {
+      FastArgs at = a;
+      const int rc = warp_tile_launch(at, n, mode, d0.C, stream);
+      if (rc != 1) return rc;
+    }
+  }
   if (d0.sampler == DMH_S1) {
     if (d0.param_kind == DMH_PARAM_HOMOGRAPHY)
-      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
-    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
+      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
+    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
   }
   if (d0.param_kind == DMH_PARAM_FLOW)
-    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, (dense ? 1 : 0) | (stage_ok ? 2 : 0) | (tile_ok ? 4 : 0), stream);
+    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
   return 1;
 }
 

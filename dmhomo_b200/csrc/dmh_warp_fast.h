@@ -33,24 +33,20 @@ struct FastArgs {
   int B, Hs, Ws, h, w;
   int tiles_x, tiles_y;
   float sx, sy;
-  // opaque identities for the packed (f32x2) kernels, see dmh_warp_pair.cu
+  // opaque identities for the packed (f32x2) kernel, see dmh_warp_tile.cu
   float one, neg_zero, minus_one;
   // tiled persistent kernel (dmh_warp_tile.cu): length of the tile list, "start offsets are benign" flag
   int n_tiles, start_sane;
-  int n_static, counter_slot;   // guided schedule: statically chunked prefix of the tile list, counter slot
-  int chunk;                    // tiles per dynamic claim
-  int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body; DMH_TILE_INTERIOR=0 for A/B checks
+  int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body (dmh_set_tuning "tile_interior")
 };
 
 // pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it
 // launched, 1 when the request is outside the lean path (caller falls back to the general kernel).
 int warp_fast_try(const dmh_warp_desc* descs, int n, int pass, cudaStream_t stream);
 
-// Paired (two rows per thread, packed fp32) form of the dense S1 forward / fused launches.
-int warp_pair_launch(FastArgs& a, int n, long long tiles, int param_kind, int pass, int C, cudaStream_t stream);
-
-// Persistent, shared-memory staged, packed form of the dense S1 homography launches (forward and fused).
-// Returns 1 when the shape is outside what it takes.
-int warp_tile_launch(FastArgs& a, int n, int pass, int C, cudaStream_t stream);
+// Persistent, TMA staged, packed-fp32 form of the dense S1 homography launches.  mode = bits 1 (warped output +
+// validity mask) | 2 (masked L1 against the target) | 4 (gradients in the same pass).  Returns 1 when the shape is
+// outside what it takes.
+int warp_tile_launch(FastArgs& a, int n, int mode, int C, cudaStream_t stream);
 
 }  // namespace dmh

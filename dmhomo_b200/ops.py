@@ -418,6 +418,31 @@ class WarpTerm:
 _SLOTS = 5  # tensors per term: src, target, param, soft_mask, sample_weight
 
 
+def _plan_grad_slots(flat, terms, needs, kind, base):
+    """(term, slot) -> (offset, numel) into one flat gradient buffer starting at `base`.
+
+    The kernels ACCUMULATE (atomics / TMA reduce-add) the gradients of src, target and of a HOMOGRAPHY / BASIS8
+    parameter, so one tensor object used in several of those slots (img1 is the target of one term and the source
+    of the other) shares one zeroed buffer and is handed back once.  Gradients of soft_mask and of a FLOW / COORDS
+    parameter are plain stores: every (term, slot) gets its own buffer and autograd sums them (the reference passes
+    one mask to both terms when params.normalize_mask is set, HEM/loss/losses.py:129).  Sharing is by tensor
+    identity, never by storage address: two distinct leaves that alias one storage each get their own gradient.
+    `flat` holds the tensors (or their ids) in apply() order."""
+    accumulated = (0, 1) + ((2,) if kind in (PARAM_HOMOGRAPHY, PARAM_BASIS8) else ())
+    slots, owners, total = {}, {}, base
+    for i, tl in enumerate(terms):
+        for s in (0, 1, 2, 3):
+            if tl[s] is None or not needs[i * _SLOTS + s]:
+                continue
+            obj = flat[i * _SLOTS + s]
+            key = (obj if isinstance(obj, int) else id(obj)) if s in accumulated else ("own", i, s)
+            if key not in owners:
+                owners[key] = (total, tl[s].numel())
+                total += tl[s].numel()
+            slots[(i, s)] = owners[key]
+    return slots, total
+
+
 class _WarpLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, basis, *flat):
@@ -443,19 +468,7 @@ class _WarpLoss(torch.autograd.Function):
         fused = bool(cfg["fused"]) and any_grad
         # one flat zeroed workspace: [loss accumulators (double) | gradients of every distinct input]
         acc_floats = 2 * n * B
-        slots = {}     # (term, slot) -> (offset, numel) into the flat gradient region
-        owners = {}    # data_ptr -> (offset, numel)   (img1 is target of one term and source of the other)
-        total = acc_floats
-        if fused:
-            for i, tl in enumerate(terms):
-                for s in (0, 1, 2, 3):
-                    if tl[s] is None or not needs[i * _SLOTS + s]:
-                        continue
-                    key = (tl[s].data_ptr(), tl[s].numel())
-                    if key not in owners:
-                        owners[key] = (total, tl[s].numel())
-                        total += tl[s].numel()
-                    slots[(i, s)] = owners[key]
+        slots, total = _plan_grad_slots(flat, terms, needs, cfg["kind"], acc_floats) if fused else ({}, acc_floats)
         ws = torch.zeros(total, device=dev, dtype=torch.float32)
         acc = ws[:acc_floats].view(torch.float64)
 
@@ -481,12 +494,14 @@ class _WarpLoss(torch.autograd.Function):
 
         ctx.cfg = dict(cfg, sx=sx, sy=sy, scale=scale, n=n, fused=fused, B=B, h=h, w=w, acc_floats=acc_floats)
         ctx.slots = slots
+        ctx.input_ids = [id(t) for t in flat]
         ctx.shapes = [None if t is None else t.shape for t in flat]
-        if fused:
-            ctx.save_for_backward(ws)
-        else:
-            ctx.save_for_backward(bas_c, per, *[t for tl in terms for t in tl])
-            ctx.none_mask = [t is None for tl in terms for t in tl]
+        # The fused pass has left the gradients (for an upstream gradient of 1) in ws: the first backward rescales them
+        # in place and hands out views.  The inputs are saved as well, so that any further backward through the same
+        # graph (retain_graph=True, checkpointing) recomputes with the separate backward kernel instead of rescaling
+        # - and possibly handing out again - buffers autograd may already own.
+        ctx.save_for_backward(bas_c, per, *[t for tl in terms for t in tl], *([ws] if fused else []))
+        ctx.consumed = False
         return loss
 
     @staticmethod
@@ -496,8 +511,9 @@ class _WarpLoss(torch.autograd.Function):
         needs = ctx.needs_input_grad[2:]
         g = _f32(g)
         dev = g.device
-        if cfg["fused"]:
-            (ws,) = ctx.saved_tensors
+        if cfg["fused"] and not ctx.consumed:
+            ctx.consumed = True
+            ws = ctx.saved_tensors[-1]
             slots = ctx.slots
             nf = ws.numel() - cfg["acc_floats"]
             if nf > 0:
@@ -507,18 +523,9 @@ class _WarpLoss(torch.autograd.Function):
         else:
             saved = list(ctx.saved_tensors)
             bas_c, per = saved[0], saved[1]
-            flat = saved[2:]
+            flat = saved[2:2 + n * _SLOTS]
             terms = [flat[i * _SLOTS:(i + 1) * _SLOTS] for i in range(n)]
-            slots, owners, total = {}, {}, 0
-            for i, tl in enumerate(terms):
-                for s in (0, 1, 2, 3):
-                    if tl[s] is None or not needs[i * _SLOTS + s]:
-                        continue
-                    key = (tl[s].data_ptr(), tl[s].numel())
-                    if key not in owners:
-                        owners[key] = (total, tl[s].numel())
-                        total += tl[s].numel()
-                    slots[(i, s)] = owners[key]
+            slots, total = _plan_grad_slots(ctx.input_ids, terms, needs, cfg["kind"], 0)
             ws = torch.zeros(max(total, 1), device=dev, dtype=torch.float32)
             cfgacc = 0
 
@@ -658,6 +665,7 @@ class _BasisWarpLoss(torch.autograd.Function):
             cur.wait_event(join2)
         ctx.cfg = (any_grad, acc_floats, n_img, off_g1, off_g2, off_wf, off_wb, B, i1.shape, w_f.shape, w_b.shape)
         ctx.save_for_backward(ws)
+        ctx.consumed = False
         ctx.mark_non_differentiable(Hf, Hb)
         return loss, Hf, Hb
 
@@ -666,6 +674,11 @@ class _BasisWarpLoss(torch.autograd.Function):
         any_grad, acc_floats, n_img, off_g1, off_g2, off_wf, off_wb, B, ishape, wfs, wbs = ctx.cfg
         if not any_grad:
             return (None,) * 6
+        if ctx.consumed:
+            raise RuntimeError("basis_warp_loss: its gradients were produced by the forward pass and have been handed "
+                               "out; a second backward through the same graph is not supported - use "
+                               "basis_homography() + warp_loss() where retain_graph=True is needed")
+        ctx.consumed = True
         (ws,) = ctx.saved_tensors
         g = _f32(g)
         dev = g.device
@@ -861,7 +874,8 @@ def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEA
             if bool(((sh[:, 0] < 0) | (sh[:, 0] + pw > W) | (sh[:, 1] < 0) | (sh[:, 1] + ph > H)).any()):
                 raise ValueError("pairs_u8_to_gray: crop window outside the image")
         st = torch.as_tensor(start, device=dev).to(torch.int32).reshape(B, 2).contiguous()
-        patch = torch.empty(B, 2, ph, pw, device=dev, dtype=torch.float32)
+        # device-resident origins are not validated on the host: pixels of a window that leaves the image stay 0
+        patch = (torch.zeros if (torch.is_tensor(start) and start.is_cuda) else torch.empty)(B, 2, ph, pw, device=dev, dtype=torch.float32)
     m3, s3 = (C.c_double * 3)(*[float(v) for v in mean]), (C.c_double * 3)(*[float(v) for v in std])
     with torch.cuda.device(dev):
         L.check(L.lib().dmh_pairs_u8_to_gray(_p(x), _p(st), _p(full), _p(patch), _p(rgb), m3, s3, B, H, W, ph, pw,

@@ -18,7 +18,8 @@
  *   - return value: DMH_OK (0) or a negative dmh_status; dmh_last_error_string()
  *     returns a thread-local description of the last failure;
  *   - buffers documented "accumulated" must be zeroed by the caller;
- *   - re-entrant, no global mutable state besides a launch counter; lazy CUDA
+ *   - re-entrant; the only process-wide state is a launch counter and the explicit
+ *     dmh_set_tuning() knobs (no environment variables are read); lazy CUDA
  *     initialisation (nothing happens at dlopen time, so the library may be loaded
  *     in forked data-loader workers).
  */
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMH_ABI_VERSION 1
+#define DMH_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DMH_API __attribute__((visibility("default")))
@@ -135,6 +136,12 @@ DMH_API uint64_t dmh_launch_count(void);
 /* Name of the kernel the calling thread launched last through this library ("" before the first launch);
  * bench.py labels its roofline object with it. */
 DMH_API const char* dmh_last_kernel_name(void);
+/* Development knobs, process-wide, read at launch time (defaults = the measured best; none changes a result):
+ *   "tile"          0 scalar kernels only | 1 TMA tile kernel for the dense C = 1 launches | 2 also C = 3 (default)
+ *   "tile_interior" bit 0 interior-tile body, bit 1 mixed-tile body of the tile kernel (default 3)
+ * The library reads no environment variables.  Unknown key: DMH_EINVAL. */
+DMH_API int dmh_set_tuning(const char* key, int value);
+DMH_API int dmh_get_tuning(const char* key, int* value);
 
 /* --- warp (A6-A9, A12-A14) -------------------------------------------------------------
  * dmh_warp_forward: get_warp_flow / transformer / WarpImages / warp / warp_with_mapping /

@@ -399,6 +399,82 @@ def test_fused_loss_soft_mask_and_flow_param():
             assert (tg.grad.cpu() - tc.grad).abs().max().item() < ATOL
 
 
+def test_fused_loss_one_mask_tensor_shared_by_both_terms():
+    """params.normalize_mask: mask_b = mask_f = mask_fusion (HEM/loss/losses.py:129) - ONE soft-mask tensor (and here
+    also one flow tensor) feeds both terms; its gradient is the sum of both terms' contributions, fused or not."""
+    B, C, h, w = 2, 1, 32, 48
+    gen = g(44)
+    f1, f2 = synth.smooth_images(B, C, h, w, gen), synth.smooth_images(B, C, h, w, gen)
+    flow = torch.randn(B, 2, h, w, generator=gen) * 3
+    m = torch.rand(B, 1, h, w, generator=gen)
+    a, b, fc, mc = [t.clone().requires_grad_(True) for t in (f1, f2, flow, m)]
+    ref = port.masked_l1(mc, a, port.get_warp_flow(b, fc)) + port.masked_l1(mc, b, port.get_warp_flow(a, fc))
+    ref.backward()
+    for fused in (True, False):
+        ag, bg, fg, mg = [t.to(DEV).requires_grad_(True) for t in (f1, f2, flow, m)]
+        loss = losses.unsup_loss(ag, bg, fg, fg, mask_f=mg, mask_b=mg, fused=fused)
+        assert abs(loss.item() - ref.item()) < 1e-5
+        loss.backward()
+        for tg, tc, name in ((ag, a, "img1"), (bg, b, "img2"), (fg, fc, "flow"), (mg, mc, "mask")):
+            assert (tg.grad.cpu() - tc.grad).abs().max().item() < ATOL, (name, fused)
+
+
+def test_fused_loss_aliasing_leaves_get_their_own_gradients():
+    """Two distinct leaves that view one storage are different inputs: each receives its own gradient."""
+    B, C, h, w = 2, 1, 32, 48
+    gen = g(45)
+    base = synth.smooth_images(B, C, h, w, gen).to(DEV)
+    other = synth.smooth_images(B, C, h, w, gen).to(DEV)
+    src = port.corner_points(B, h, w)
+    H = port.dlt4(src, src + synth.corner_offsets(B, 4.0, gen)).to(DEV)
+    x1 = base.detach().requires_grad_(True)
+    x2 = base.detach().requires_grad_(True)        # same storage, different leaf
+    assert x1.data_ptr() == x2.data_ptr()
+    loss = ops.warp_loss([ops.WarpTerm(x1, other, H), ops.WarpTerm(other, x2, H)], kind=ops.PARAM_HOMOGRAPHY)
+    loss.backward()
+    assert x1.grad is not None and x2.grad is not None
+    y = base.clone().requires_grad_(True)
+    ops.warp_loss([ops.WarpTerm(y, other, H)], kind=ops.PARAM_HOMOGRAPHY).backward()
+    assert (x1.grad - y.grad).abs().max().item() < 1e-7      # source-side gradient only
+    z = base.clone().requires_grad_(True)
+    ops.warp_loss([ops.WarpTerm(other, z, H)], kind=ops.PARAM_HOMOGRAPHY).backward()
+    assert (x2.grad - z.grad).abs().max().item() < 1e-7      # target-side gradient only
+
+
+def test_fused_loss_second_backward_with_retain_graph():
+    """retain_graph=True with a non-unit loss scale: the second backward must not rescale (or hand out again) the
+    buffers of the first; basis_warp_loss refuses a second backward loudly."""
+    B, C, h, w = 2, 1, 40, 64
+    img1, img2, off_f, _ = _pipeline_inputs(B, C, h, w, 5.0, 46, smooth=True)
+    src = port.corner_points(B, h, w)
+    H = port.dlt4(src, src + off_f).to(DEV)
+    i2 = img2.to(DEV).requires_grad_(True)
+    loss = ops.warp_loss([ops.WarpTerm(i2, img1.to(DEV), H)], kind=ops.PARAM_HOMOGRAPHY, fused=True)
+    (loss * 3.0).backward(retain_graph=True)
+    g1 = i2.grad.clone()
+    i2.grad = None
+    (loss * 3.0).backward()
+    assert (i2.grad - g1).abs().max().item() < 1e-7
+    i2c = img2.clone().requires_grad_(True)
+    flow = port.homography_to_flow(H.cpu(), h, w)[0]
+    (3.0 * port.masked_l1(port.border_mask(flow).unsqueeze(1), img1, port.get_warp_flow(i2c, flow))).backward()
+    assert (g1.cpu() - i2c.grad).abs().max().item() < 1e-6
+    # accumulation into .grad across the two backwards (autograd may have adopted the first buffer as .grad)
+    i2b = img2.to(DEV).requires_grad_(True)
+    loss = ops.warp_loss([ops.WarpTerm(i2b, img1.to(DEV), H)], kind=ops.PARAM_HOMOGRAPHY, fused=True)
+    (loss * 3.0).backward(retain_graph=True)
+    (loss * 3.0).backward()
+    assert (i2b.grad - 2 * g1).abs().max().item() < 1e-6
+
+    basis = hem_utils.gen_basis(h, w).to(DEV)
+    wf = synth.basis_weights(B, g(47), 2.0).to(DEV).requires_grad_(True)
+    wb = synth.basis_weights(B, g(48), 2.0).to(DEV).requires_grad_(True)
+    l2 = ops.basis_warp_loss(basis, img1.to(DEV), img2.to(DEV), wf, wb)
+    l2.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        l2.backward()
+
+
 def test_dgm_photo_loss():
     B, C, h, w = 3, 3, 32, 32
     gen = g(43)

@@ -4,7 +4,7 @@ The dense S1 homography launches (forward: warped image + validity mask; fused: 
 of C = 1 images go through the tiled kernel by default.  These cases aim at its own machinery: partial tile
 rows / columns, fewer tiles than CTAs, the dynamic tail of the tile schedule, windows that do not cover the
 tile (global fallback taps), homographies outside the packed division's proven domain (scalar __fdiv_rn
-path), start offsets, and - in a subprocess with DMH_TILE=2 - the C = 3 instantiation.
+path), start offsets, and - in a subprocess with DMH_TUNING=tile=2 / tile=1 - the C = 3 instantiation.
 Bars: warped pixels and masks bit-exact, loss / gradients within 1e-4 absolute (north_star).
 """
 import os
@@ -145,14 +145,14 @@ torch.save(dict(out=out.cpu(), mask=mask.cpu(), loss=loss.detach().cpu(), g1=i1.
 
 
 def test_tile_interior_body_matches_general_body(tmp_path):
-    """A/B in subprocesses: DMH_TILE_INTERIOR=0 forces every tile through the general (clamping, masking) body,
+    """A/B in subprocesses: DMH_TUNING=tile_interior=0 forces every tile through the general (clamping, masking) body,
     1 allows whole interior tiles only, 3 (default) adds the per-row-pair vote inside border tiles.
     Forward output, mask and dL/dtarget (no atomics involved) must be bit-identical; the scattered dL/dsrc and the
     reductions only differ by fp32 summation order."""
     res = []
     for flag in ("3", "1", "0"):   # interior + mixed (default) / interior only / general body only
         path = str(tmp_path / f"ab{flag}.pt")
-        env = dict(os.environ, DMH_TILE_INTERIOR=flag)
+        env = dict(os.environ, DMH_TUNING="tile_interior=" + flag)
         r = subprocess.run([sys.executable, "-c", _AB_SCRIPT % ROOT, path], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         res.append(torch.load(path))
@@ -244,6 +244,6 @@ print("C3 OK")
 
 
 def test_tile_c3_instantiation_in_subprocess():
-    env = dict(os.environ, DMH_TILE="2")
+    env = dict(os.environ, DMH_TUNING="tile=2")
     r = subprocess.run([sys.executable, "-c", _C3_SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "C3 OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -8,14 +8,14 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/smoke.log
 timeout 600 python bench.py > $O/bench_cfg2.json 2> $O/bench_cfg2.err; echo "bench cfg2 rc=$?"; tail -c 1500 $O/bench_cfg2.json
-DMH_TILE=0 timeout 600 python bench.py --no-cpu-baseline > $O/bench_cfg2_scalar.json 2>/dev/null; tail -c 600 $O/bench_cfg2_scalar.json
+DMH_TUNING=tile=0 timeout 600 python bench.py --no-cpu-baseline > $O/bench_cfg2_scalar.json 2>/dev/null; tail -c 600 $O/bench_cfg2_scalar.json
 timeout 600 python bench.py --workload cfg4 --steps 10 > $O/bench_cfg4.json 2> $O/bench_cfg4.err; echo "bench cfg4 rc=$?"; tail -c 1500 $O/bench_cfg4.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2>&1; tail -c 800 $O/bench_ref.json
 if [ -x tools/tile_bench ]; then
   tools/tile_bench 64 1 320 576 32 20 > $O/tile_bench.txt 2>&1
   tools/tile_bench 64 1 320 576 32 20 1 >> $O/tile_bench.txt 2>&1
   tools/tile_bench 128 3 512 512 32 10 >> $O/tile_bench.txt 2>&1
-  DMH_TILE=2 tools/tile_bench 128 3 512 512 32 10 >> $O/tile_bench.txt 2>&1
+  tools/tile_bench 128 3 512 512 32 10 tile=2 >> $O/tile_bench.txt 2>&1
   tools/tile_bench 16 3 1080 1920 64 10 1 >> $O/tile_bench.txt 2>&1
   cat $O/tile_bench.txt
 fi

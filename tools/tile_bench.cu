@@ -4,7 +4,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/tile_bench tools/tile_bench.cu \
 //        -Ldmhomo_b200 -ldmhomo -Xlinker -rpath -Xlinker '$ORIGIN/../dmhomo_b200'
-//   tools/tile_bench [B C h w rho iters fwd_only]
+//   tools/tile_bench [B C h w rho iters fwd_only [key=value ...]]     (key=value: dmh_set_tuning knobs, e.g. tile=0)
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -41,6 +41,12 @@ int main(int argc, char** argv) {
   if (argc > 5) rho = (float)atof(argv[5]);
   if (argc > 6) iters = atoi(argv[6]);
   if (argc > 7) fwd_only = atoi(argv[7]);
+  for (int i = 8; i < argc; ++i) {   // key=value development knobs (dmh_set_tuning)
+    char* eq = strchr(argv[i], '=');
+    if (!eq) continue;
+    *eq = 0;
+    if (dmh_set_tuning(argv[i], atoi(eq + 1))) { printf("tuning: %s\n", dmh_last_error_string()); return 1; }
+  }
   const size_t plane = (size_t)h * w, img = (size_t)B * C * plane;
 
   float *i1, *i2, *g1, *g2, *o1, *o2, *Hf, *Hb, *gHf, *gHb, *src, *dst, *flush;
