@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the homography-warp hot path (BASELINE.json).
+"""bench.py - the homography-warp hot path on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg1|cfg4|cfg5] [--configs cfg1,cfg2_direct,cfg2_dropin,cfg3,cfg4,cfg5 | none]
 
-A "step" is one pass of the hot path over one batch of synthetic pairs: 8-basis weights ->
-corner offsets -> 8x8 DLT -> per-pixel homography flow -> bidirectional bilinear warp + validity
-mask -> masked L1 -> backward to both images and to the basis weights (cfg 2, the config the
-metric is quoted on; --workload cfg4 = 3x512x512 pairs from 4-pt offsets).  Output pixels of both
-warp directions are the unit: value = Gpix/s over all ranks.
+The JSON line is the headline workload (default cfg2, the config BASELINE.json's metric is quoted on: 8-basis
+weights -> corner offsets -> 8x8 DLT -> per-pixel homography flow -> bidirectional bilinear warp + validity mask ->
+masked L1 -> backward to both images and to the basis weights).  A "step" is one such pass over one batch of
+synthetic pairs; output pixels of both warp directions are the unit: value = Gpix/s over all ranks.  The other
+BASELINE configs (and the two other forms of cfg2: the reference's own "direct" basis-flow variant and the drop-in
+call sequence) ride along under "configs", each with its own value / kernel / kernel_ms / roofline.
 
-Multi-GPU (torchrun, one rank per GPU): the batch is sharded, every rank runs the same per-GPU
-batch (weak scaling); the only exchange is the scalar-loss all-reduce (NCCL), inside the step.
+Multi-GPU (torchrun, one rank per GPU): the batch is sharded.  cfg2 / cfg1 / cfg3 keep the per-GPU batch (weak
+scaling); cfg4 (4096 pairs) and cfg5 (8192 frames) split the fixed job over the ranks (strong scaling).  The only
+exchange is the scalar loss / count all-reduce (NCCL), accumulated on the device and reduced every --reduce-every
+steps (the reference gathers its scalars at logging / evaluation time only, hem_evaluate.py:132-151).
 """
 import argparse
 import json
+import math
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -30,13 +36,21 @@ METRIC = "Gpix/s homography DLT+flow+warp fwd/bwd at 1/2/4/8 B200; % HBM peak"
 UNIT = "Gpix/s"
 N_SETS = 4  # rotating input sets so that no step finds its inputs in the 126 MB L2
 
+# algorithmic bytes / output pixel / direction: forward warp 8C (+1 mask), evaluation 12C+1,
+# train fwd+bwd 24C+1, +16 with an explicit flow tensor
 WORKLOADS = {
-    # per-GPU batch; algorithmic bytes / output pixel / direction for train fwd+bwd = 24C+1
-    "cfg2": dict(B=64, C=1, h=320, w=576, param="basis8->corner offsets->DLT", bytes_per_px=25,
+    "cfg1": dict(B=16, C=1, h=360, w=640, rho=32.0, bytes_per_px=13, scaling="weak", sets=8,
+                 desc="cfg1: B=16 pairs 1x360x640, 4-pt H -> bidirectional S1 warp + M1 mask + masked L1, forward only (HEM evaluation)"),
+    "cfg2": dict(B=64, C=1, h=320, w=576, rho=32.0, bytes_per_px=25, scaling="weak", sets=N_SETS,
                  desc="cfg2: B=64 pairs 1x320x576, 8-basis flow -> DLT -> bidirectional S1 warp + M1 mask + masked L1, fwd+bwd"),
-    "cfg4": dict(B=512, C=3, h=512, w=512, param="4pt offsets->DLT", bytes_per_px=73,
-                 desc="cfg4 shard: 512 pairs 3x512x512 per GPU (4096 pairs / 8), 4-pt H -> bidirectional S1 warp + M1 + L1, fwd+bwd"),
+    "cfg3": dict(B=25, C=3, h=256, w=256, rho=16.0, bytes_per_px=84, scaling="weak", sets=8,
+                 desc="cfg3: DGM condition rendering, 25 x 3x256x256: warpPerspective (cv2-exact) + fp64 homography->flow + flow->RGB + flow_warp (S3)"),
+    "cfg4": dict(B=4096, C=3, h=512, w=512, rho=32.0, bytes_per_px=73, scaling="strong", sets=1,
+                 desc="cfg4: 4096 pairs 3x512x512 batch-sharded, 4-pt H -> bidirectional S1 warp + M1 + L1, fwd+bwd"),
+    "cfg5": dict(B=8192, C=3, h=1080, w=1920, rho=64.0, bytes_per_px=25, scaling="strong", sets=1, chunk=512,
+                 desc="cfg5: 8192 frames 3x1080x1920 sharded, one random H per frame, forward S1 warp + M1 mask, resident chunks of 512 frames"),
 }
+DEFAULT_CONFIGS = "cfg1,cfg2_direct,cfg2_dropin,cfg3,cfg4,cfg5"
 
 
 def parse():
@@ -45,18 +59,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--variant", default="dlt", choices=["dlt", "direct"], help="cfg2: 8-basis flow -> DLT -> H (graded) or the basis flow itself (net.py:817-818)")
+    ap.add_argument("--api", default="fused", choices=["fused", "dropin"], help="cfg2: fused ops or the reference's call sequence through compat.*")
+    ap.add_argument("--configs", default=DEFAULT_CONFIGS, help="comma list of side configs reported under 'configs' ('none' to skip)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="pairs per CPU-baseline / reference-arm step")
+    ap.add_argument("--reduce-every", type=int, default=10, help="steps between loss all-reduces (multi-GPU)")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step block until this much time is covered")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--one-op", action="store_true",
-                    help="cfg2 step through the one-op ops.basis_warp_loss() (forked stream branches) instead of "
-                         "basis_homography() + warp_loss(); measured equal (169.2 vs 169.0 us per step)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tuning", default="", help="dmh_set_tuning knobs, e.g. tile=1,tile_interior=0")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks
+# clocks, NUMA
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -111,8 +129,31 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(dev_index):
+    """Pin this process (and hence the pinned host buffers it first-touches) to the CPUs of the NUMA node the GPU hangs
+    off: with eight ranks on one host the H2D copies otherwise cross the socket interconnect.  Best effort; returns
+    {"node", "cpus", "previous"} (previous = the affinity to restore for the CPU leg) or None."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        previous = sorted(os.sched_getaffinity(0))
+        allowed = sorted(set(cpus) & set(previous))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "previous": previous}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores
+# CPU arm: the reference's algorithm (oracle port) on the host cores - one function, one statistic, both legs
 # ------------------------------------------------------------------------------------------------
 def cpu_step_fn(workload, sample):
     """Returns (fn, pixels_per_call, description).  Executes oracle/ - allowed here only."""
@@ -133,16 +174,44 @@ def cpu_step_fn(workload, sample):
             for t in (img1, img2, wf, wb):
                 t.grad = None
             return port.pipeline_basis(img1, img2, basis, wf, wb, variant="dlt", backward=True)["loss"].item()
+        what = "fwd+bwd"
     else:
-        off_f = synth.corner_offsets(sample, 32.0, gen).requires_grad_(True)
-        off_b = synth.corner_offsets(sample, 32.0, gen).requires_grad_(True)
+        off_f = synth.corner_offsets(sample, wl["rho"], gen).requires_grad_(True)
+        off_b = synth.corner_offsets(sample, wl["rho"], gen).requires_grad_(True)
+        bwd = workload == "cfg4"
 
         def fn():
             for t in (img1, img2, off_f, off_b):
                 t.grad = None
-            return port.pipeline_h4pt(img1, img2, off_f, off_b, backward=True)["loss"].item()
+            return port.pipeline_h4pt(img1, img2, off_f, off_b, backward=bwd)["loss"].item()
+        what = "fwd+bwd" if bwd else "forward"
 
-    return fn, 2 * sample * h * w, f"{sample} of {wl['B']} pairs of {workload} per step, fwd+bwd, torch-CPU port of the reference"
+    return fn, 2 * sample * h * w, f"{sample} of {wl['B']} pairs of {workload} per step, {what}, torch-CPU port of the reference"
+
+
+def time_cpu(fn, min_passes=5, budget_s=10.0, max_passes=50):
+    """Median seconds per pass over >= min_passes passes (about budget_s of CPU work)."""
+    fn()
+    times, t_start = [], time.perf_counter()
+    while len(times) < min_passes or (time.perf_counter() - t_start < budget_s and len(times) < max_passes):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > 3 * budget_s:
+            break
+    return statistics.median(times), len(times)
+
+
+def static_config(args, workload, world):
+    """The keys both arms print: what is measured, not how a particular run went."""
+    wl = WORKLOADS[workload]
+    strong = wl["scaling"] == "strong"
+    per_gpu = wl["B"] // world if strong else wl["B"]
+    sets = wl["sets"]
+    return {"workload": wl["desc"], "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
+            "parallelism": f"batch-sharded x{world}",
+            "variant": (args.variant if workload == "cfg2" else "4pt"), "api": args.api if workload == "cfg2" else "fused",
+            "l2": (f"{sets} rotating input sets" if sets > 1 else "one resident input set") + " larger than the 126 MB L2"}
 
 
 def run_reference(args):
@@ -153,18 +222,21 @@ def run_reference(args):
     fn, px, what = cpu_step_fn(args.workload, args.cpu_sample)
     for _ in range(max(args.warmup, 1)):
         fn()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         fn()
-    dt = time.perf_counter() - t0
-    val = px * args.steps / dt / 1e9
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    val = px / med / 1e9
     wl = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "sample": what},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": what},
+        "config": static_config(args, args.workload, max(args.gpus, 1)),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": what + f", median of {len(times)} passes"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,60 +244,140 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# our arm
+# our arm: workloads
 # ------------------------------------------------------------------------------------------------
-class PairStep:
-    """Static buffers + the step of one workload on one GPU."""
+class Ctx:
+    """Per-process state shared by the workloads."""
 
-    def __init__(self, workload, dev, rank, two_calls=False):
+    def __init__(self, args):
+        from dmhomo_b200 import dist as ddist
+        import torch.distributed as tdist
+
+        self.args = args
+        self.rank, self.local_rank, self.world = ddist.init("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        self.tdist = tdist
+        self.stream = torch.cuda.Stream(self.dev)
+        self.peak, self.peak_src = self._peak()
+
+    def _peak(self):
+        path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(path):
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+    def barrier(self):
+        if self.world > 1:
+            self.tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(values, device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.tdist.all_reduce(t, op=self.tdist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def traffic_for(key):
+    """dram__bytes per launch of the dominant kernel from the committed ncu pass (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(key)
+    except Exception:
+        return None
+
+
+def roofline(ctx, bytes_per_px, pixels, kernel_ms, kernel, traffic_key=None):
+    if not kernel_ms or kernel_ms <= 0:
+        return None
+    alg = bytes_per_px * pixels
+    ach = alg / (kernel_ms * 1e-3) / 1e9
+    tr = traffic_for(traffic_key) if traffic_key else None
+    r = {"bound": "hbm", "achieved": ach, "peak": ctx.peak, "unit": "GB/s", "frac": ach / ctx.peak, "traffic": tr, "kernel": kernel,
+         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg, "peak_source": ctx.peak_src}
+    if tr:
+        r["dram_gbs"] = tr / (kernel_ms * 1e-3) / 1e9     # measured DRAM bytes (ncu pass) over the live kernel time
+        r["dram_frac"] = r["dram_gbs"] / ctx.peak
+    return r
+
+
+class Step:
+    """One workload on one GPU: static buffers + step(k, ev).  ev = (begin, end) events recorded tightly around the
+    dominant kernel.  pixels = output pixels per step on this rank."""
+    graphable = True
+    has_loss = True
+    kernel_name = ""
+
+    def zero_grads(self):
+        pass
+
+
+class PairStep(Step):
+    """cfg2 (8 basis weights) and cfg4 (4-pt offsets): bidirectional warp + mask + masked L1, fwd+bwd."""
+
+    def __init__(self, ctx, workload, B, variant="dlt", api="fused"):
         from dmhomo_b200 import ops, synth
-        from dmhomo_b200.compat import hem_utils
+        from dmhomo_b200.compat import flow_and_mapping_operations as fmo, hem_utils, losses
 
-        self.ops = ops
-        self.two_calls = two_calls   # cfg2 through basis_homography() + warp_loss() instead of basis_warp_loss()
+        self.ops, self.hem_utils, self.fmo, self.losses = ops, hem_utils, fmo, losses
         wl = WORKLOADS[workload]
-        self.wl, self.workload, self.dev = wl, workload, dev
-        B, C, h, w = wl["B"], wl["C"], wl["h"], wl["w"]
-        self.B, self.C, self.h, self.w = B, C, h, w
-        gen = torch.Generator(device=dev).manual_seed(synth.SEED + rank)
-        self.sets = []
-        for _ in range(N_SETS):
-            img1 = torch.rand(B, C, h, w, generator=gen, device=dev).requires_grad_(True)
-            img2 = torch.rand(B, C, h, w, generator=gen, device=dev).requires_grad_(True)
+        dev = ctx.dev
+        self.workload, self.variant, self.api = workload, variant, api
+        self.B, self.C, self.h, self.w = B, wl["C"], wl["h"], wl["w"]
+        C, h, w = self.C, self.h, self.w
+        gen = torch.Generator(device=dev).manual_seed(synth.SEED + ctx.rank)
+        self.sets, self.pairs = [], []
+        for _ in range(wl["sets"]):
+            pair = torch.rand(2, B, C, h, w, generator=gen, device=dev)    # image 1 / image 2 of every pair: two dense batches
+            img1, img2 = pair[0].detach().requires_grad_(True), pair[1].detach().requires_grad_(True)
             if workload == "cfg2":
-                par = tuple(((torch.rand(B, 8, generator=gen, device=dev) * 2 - 1) * 4.0).requires_grad_(True)
-                            for _ in range(2))
+                par = tuple(((torch.rand(B, 8, generator=gen, device=dev) * 2 - 1) * 4.0).requires_grad_(True) for _ in range(2))
             else:
-                par = ((torch.rand(2 * B, 4, 2, generator=gen, device=dev) * 2 - 1) * 32.0).requires_grad_(True)
-            self.sets.append((img1, img2) + (par if isinstance(par, tuple) else (par,)))
+                par = (((torch.rand(2 * B, 4, 2, generator=gen, device=dev) * 2 - 1) * wl["rho"]).requires_grad_(True),)
+            self.pairs.append(pair)
+            self.sets.append((img1, img2) + par)
         self.basis = hem_utils.gen_basis(h, w).to(dev) if workload == "cfg2" else None
+        self.basis_ref = self.basis.reshape(1, 8, -1) if self.basis is not None else None   # the reference's (1,8,2hw) view
         self.src2 = synth.corner_points(2 * B, h, w, dev)
         self.pixels = 2 * B * h * w
-        self.loss_vec = torch.zeros(2, device=dev, dtype=torch.float64)
-        self.ev = None  # (begin, end) events around the dominant kernel, set per timed step
+        explicit_flow = workload == "cfg2" and (variant == "direct" or api == "dropin")
+        self.bytes_per_px = 24 * C + (17 if explicit_flow else 1)
+        self.l1 = losses.LossL1(reduction="mean")
 
-    def forward_backward(self, k, ev=None):
+    def step(self, k, ev=None):
         ops = self.ops
         img1, img2, *par = self.sets[k]
         B, h, w = self.B, self.h, self.w
-        if self.workload == "cfg2" and not self.two_calls:
-            # the whole step as one op: weights -> H || workspace zeroing, fused warp, loss finish || adjoint DLT
+        if self.workload == "cfg2" and self.api == "dropin":
+            # the reference's own statements (HEM/model/net.py:808-818, HEM/loss/losses.py:142-146) with the patched
+            # names: the basis product and the mask * image products are inline torch in the reference and stay torch
+            hu, fmo = self.hem_utils, self.fmo
+            flow_f = (self.basis_ref * par[0].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
+            flow_b = (self.basis_ref * par[1].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
             ops.warp_timing_events = ev
-            loss = ops.basis_warp_loss(self.basis, img1, img2, par[0], par[1])
+            w2 = hu.get_warp_flow(img2, flow_f)
             self.kernel_name = ops.last_warp_kernel
             ops.warp_timing_events = None
+            w1 = hu.get_warp_flow(img1, flow_b)
+            m_f = fmo.create_border_mask(flow_f).unsqueeze(1)
+            m_b = fmo.create_border_mask(flow_b).unsqueeze(1)
+            loss = self.l1(m_f * img1, m_f * w2) + self.l1(m_b * img2, m_b * w1)
             loss.backward()
             return loss
-        if self.workload == "cfg2":
-            # 8 basis weights -> corner offsets -> DLT, both directions, one launch
-            Hf, Hb = ops.basis_homography(self.basis, h, w, par[0], par[1])
+        if self.workload == "cfg2" and self.variant == "direct":
+            flow_f = ops.basis_combine(self.basis, par[0], h, w)
+            flow_b = ops.basis_combine(self.basis, par[1], h, w)
+            terms, kind = [ops.WarpTerm(img2, img1, flow_f), ops.WarpTerm(img1, img2, flow_b)], ops.PARAM_FLOW
         else:
-            H = ops.dlt4(self.src2, self.src2 + par[0])
-            Hf, Hb = H[:B], H[B:]
+            if self.workload == "cfg2":
+                Hf, Hb = ops.basis_homography(self.basis, h, w, par[0], par[1])   # weights -> corner offsets -> DLT, one launch
+            else:
+                H = ops.dlt4(self.src2, self.src2 + par[0])
+                Hf, Hb = H[:B], H[B:]
+            terms, kind = [ops.WarpTerm(img2, img1, Hf), ops.WarpTerm(img1, img2, Hb)], ops.PARAM_HOMOGRAPHY
         ops.warp_timing_events = ev   # recorded tightly around the fused warp launch (no memset, no loss_finish)
-        loss = ops.warp_loss([ops.WarpTerm(img2, img1, Hf), ops.WarpTerm(img1, img2, Hb)],
-                             kind=ops.PARAM_HOMOGRAPHY, sampler=ops.S1, loss_form=ops.LOSS_MASKED_DIFF,
-                             border_mask=True, fused=True)
+        loss = ops.warp_loss(terms, kind=kind, sampler=ops.S1, loss_form=ops.LOSS_MASKED_DIFF, border_mask=True, fused=True)
         self.kernel_name = ops.last_warp_kernel
         ops.warp_timing_events = None
         loss.backward()
@@ -236,264 +388,624 @@ class PairStep:
             for t in s:
                 t.grad = None
 
+    def kernel_label(self):
+        if self.api == "dropin":
+            return f"{self.kernel_name}<S1,FLOW,FWD,C={self.C}> (first get_warp_flow of the call sequence)"
+        kind = "FLOW" if self.variant == "direct" and self.workload == "cfg2" else "HOMOGRAPHY"
+        return f"{self.kernel_name}<S1,{kind},FUSED,C={self.C},MASKED_DIFF,dense> (both directions, one launch)"
 
-def run_ours(args):
-    from dmhomo_b200 import _lib, dist as ddist
 
-    rank, local_rank, world = ddist.init("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    import torch.distributed as tdist
+class EvalStep(Step):
+    """cfg1: the evaluation pass - 4-pt DLT, both warps, both masks and the masked L1, forward only."""
 
-    # DMH_FORCE_DIST=1: exercise the multi-rank step (loss all-reduce inside the graph) on a single rank
-    dist_step = world > 1
-    if os.environ.get("DMH_FORCE_DIST") and world == 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        tdist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
-        dist_step = True
+    def __init__(self, ctx, B):
+        from dmhomo_b200 import ops, synth
 
-    wl = WORKLOADS[args.workload]
-    st = PairStep(args.workload, dev, rank, two_calls=not args.one_op)
-    K, W = args.steps, max(args.warmup, 3)
-    stream = torch.cuda.Stream(dev)
+        self.ops = ops
+        wl = WORKLOADS["cfg1"]
+        dev = ctx.dev
+        self.B, self.C, self.h, self.w = B, wl["C"], wl["h"], wl["w"]
+        gen = torch.Generator(device=dev).manual_seed(synth.SEED + ctx.rank)
+        self.sets = []
+        for _ in range(wl["sets"]):
+            img1 = torch.rand(B, self.C, self.h, self.w, generator=gen, device=dev)
+            img2 = torch.rand(B, self.C, self.h, self.w, generator=gen, device=dev)
+            off = (torch.rand(2 * B, 4, 2, generator=gen, device=dev) * 2 - 1) * wl["rho"]
+            self.sets.append((img1, img2, off))
+        self.src2 = synth.corner_points(2 * B, self.h, self.w, dev)
+        self.pixels = 2 * B * self.h * self.w
+        self.bytes_per_px = wl["bytes_per_px"]
 
-    red_base = torch.tensor([0.0, float(st.B)], device=dev)
-    red_scale = torch.tensor([float(st.B), 0.0], device=dev)
-    red_vecs = [torch.zeros(2, device=dev) for _ in range(N_SETS)]
-    comm_stream = torch.cuda.Stream(dev)
-    step_done = [torch.cuda.Event() for _ in range(N_SETS)]
-    comm_done = [torch.cuda.Event() for _ in range(N_SETS)]
-
-    def reduce_loss(loss, k):
-        """The path's only exchange: one all-reduce(sum) of {loss * count, count}; the global
-        mean is red_vecs[k][0] / red_vecs[k][1].  One tiny kernel + one NCCL call, on a second stream behind the step's
-        event so that the next step's kernels do not wait for the collective's latency (nothing downstream of the
-        step consumes the reduced scalar); the compute stream waits for it before the same input set is reused, and
-        the timed region ends with a full device synchronize.  Issued eagerly, never captured: NCCL collectives
-        inside a CUDA graph hang on this stack (tools/dist_probe.py --graph, NCCL 2.28.9 / torch 2.11) with > 1 rank."""
-        cur = torch.cuda.current_stream(dev)
-        step_done[k].record(cur)
-        comm_stream.wait_event(step_done[k])
-        loss.record_stream(comm_stream)
-        with torch.cuda.stream(comm_stream):
-            torch.addcmul(red_base, red_scale, loss.detach().expand(2), out=red_vecs[k])
-            tdist.all_reduce(red_vecs[k])
-            comm_done[k].record(comm_stream)
-
-    def step_eager(k, ev=None):
-        st.zero_grads()
-        loss = st.forward_backward(k, ev)
-        if dist_step:
-            reduce_loss(loss, k)
+    def step(self, k, ev=None):
+        ops = self.ops
+        img1, img2, off = self.sets[k]
+        with torch.no_grad():
+            H = ops.dlt4(self.src2, self.src2 + off)
+            ops.warp_timing_events = ev
+            loss, _, _ = ops.warp_eval([ops.WarpTerm(img2, img1, H[:self.B]), ops.WarpTerm(img1, img2, H[self.B:])],
+                                       kind=ops.PARAM_HOMOGRAPHY, masks_as_bool=False)
+            self.kernel_name = ops.last_warp_kernel
+            ops.warp_timing_events = None
         return loss
 
-    graphs, g_loss, g_events, launches_per_step = [], [], [], None
+    def kernel_label(self):
+        return f"{self.kernel_name}<S1,HOMOGRAPHY,OUT+LOSS,C=1> (both directions, one launch: warped + mask + loss)"
+
+
+class RenderStep(Step):
+    """cfg3: DGM condition rendering (ddpm.py:1520-1540, 1471-1502, 1262-1280) for a 25-sample batch."""
+    has_loss = False
+
+    def __init__(self, ctx, B):
+        from dmhomo_b200 import ops, synth
+        from dmhomo_b200.compat import dgm
+
+        self.ops = ops
+        wl = WORKLOADS["cfg3"]
+        dev = ctx.dev
+        self.B, self.C, self.h, self.w = B, wl["C"], wl["h"], wl["w"]
+        gen = torch.Generator(device=dev).manual_seed(synth.SEED + ctx.rank)
+        cpu_gen = synth.generator(ctx.rank)
+        self.sets = []
+        for _ in range(wl["sets"]):
+            im2 = torch.rand(B, self.C, self.h, self.w, generator=gen, device=dev)
+            H360 = synth.homographies_360x640(B, cpu_gen, wl["rho"] * 2)
+            homo = torch.stack([torch.from_numpy(dgm.adapt_homography_to_preprocessing_v3(360, 640, H360[b], self.h, self.w))
+                                for b in range(B)]).to(dev)
+            self.sets.append((im2, homo))
+        self.pixels = B * self.h * self.w
+        self.bytes_per_px = wl["bytes_per_px"]
+        self.kernel_name = "warp_perspective_kernel"
+
+    def ops_list(self, k):
+        ops = self.ops
+        im2, homo = self.sets[k]
+        h, w = self.h, self.w
+        st = {}
+
+        def s4():
+            st["warp"] = ops.warp_perspective(im2, homo, (w, h))
+
+        def flow():
+            st["flow"] = ops.homography_to_flow_f64(homo, h, w, eps=1e-6, channels_last=False)
+
+        def rgb():
+            st["rgb"] = ops.flow_to_rgb(st["flow"], 256.0)
+
+        def s3():
+            st["fw"] = ops.warp(im2, st["flow"], kind=ops.PARAM_FLOW, sampler=ops.S3_BORDER)
+
+        return [("warpPerspective (cv2-exact S4)", s4, 8 * self.C), ("homo_to_flow fp64->fp32", flow, 8),
+                ("flow_to_image", rgb, 20), ("flow_warp (S3 border)", s3, 8 * self.C + 8)]
+
+    def step(self, k, ev=None):
+        with torch.no_grad():
+            for i, (_, fn, _) in enumerate(self.ops_list(k)):
+                if ev is not None and i == 0:
+                    ev[0].record()
+                fn()
+                if ev is not None and i == 0:
+                    ev[1].record()
+        return None
+
+    def kernel_label(self):
+        return "warp_perspective_kernel (cv2-exact S4, fp64 fixed-point coordinates)"
+
+
+class FrameStep(Step):
+    """cfg5: frames_per_rank 1080p RGB frames, one random H each, forward S1 warp + M1 mask, in resident chunks."""
+    graphable = False
+    has_loss = False
+
+    def __init__(self, ctx, frames):
+        from dmhomo_b200 import ops, synth
+
+        self.ops = ops
+        wl = WORKLOADS["cfg5"]
+        dev = ctx.dev
+        self.C, self.h, self.w = wl["C"], wl["h"], wl["w"]
+        self.frames = frames
+        self.chunk = min(wl["chunk"], frames)
+        self.n_chunks = (frames + self.chunk - 1) // self.chunk
+        gen = torch.Generator(device=dev).manual_seed(synth.SEED + ctx.rank)
+        F = self.chunk
+        self.src = torch.rand(F, self.C, self.h, self.w, generator=gen, device=dev)
+        self.out = torch.empty_like(self.src)
+        self.valid = torch.empty(F, self.h, self.w, device=dev, dtype=torch.uint8)
+        corners = synth.corner_points(F, self.h, self.w, dev)
+        self.H = [ops.dlt4(corners, corners + (torch.rand(F, 4, 2, generator=gen, device=dev) * 2 - 1) * wl["rho"])
+                  for _ in range(min(self.n_chunks, 4))]
+        self.pixels = frames * self.h * self.w
+        self.bytes_per_px = wl["bytes_per_px"]
+
+    def step(self, k, ev=None):
+        ops = self.ops
+        left = self.frames
+        for c in range(self.n_chunks):
+            n = min(self.chunk, left)
+            left -= n
+            if ev is not None and c == 0:
+                ops.warp_timing_events = ev
+            ops.warp_into(self.src[:n], self.H[c % len(self.H)][:n], self.out[:n], self.valid[:n], kind=ops.PARAM_HOMOGRAPHY)
+            self.kernel_name = ops.last_warp_kernel
+            ops.warp_timing_events = None
+        return None
+
+    def kernel_pixels(self):
+        return min(self.chunk, self.frames) * self.h * self.w
+
+    def kernel_label(self):
+        return f"{self.kernel_name}<S1,HOMOGRAPHY,OUT,C=3> (one resident chunk of {min(self.chunk, self.frames)} frames per launch)"
+
+
+# ------------------------------------------------------------------------------------------------
+# measurement
+# ------------------------------------------------------------------------------------------------
+class LossReducer:
+    """The path's only exchange: the all-reduce(sum) of {sum over steps of local mean loss * local count, count}
+    (SURVEY.md section 8e).  The numerator is accumulated on the device (one tiny kernel per step, captured into the
+    step's CUDA graph), the count is known on the host; both are reduced over NCCL every `every` steps on a second
+    stream and at the end of every timed block - the reference gathers its scalars at logging / evaluation time only
+    (hem_evaluate.py:132-151, HEM/common/manager.py:51-55).  The global mean is out[0] / out[1].  Single rank: nothing
+    to exchange, nothing is launched."""
+
+    def __init__(self, ctx, count, every):
+        self.ctx, self.every, self.n, self.count = ctx, max(1, every), 0, float(count)
+        dev = ctx.dev
+        self.active = ctx.world > 1
+        self.acc = torch.zeros(1, device=dev)
+        self.out = torch.zeros(2, device=dev)
+        self.comm = torch.cuda.Stream(dev)
+        self.done = torch.cuda.Event()
+        self.collectives = 0
+
+    def accumulate(self, loss):
+        """Device side of a step (capturable)."""
+        if self.active:
+            self.acc.add_(loss.detach().reshape(1), alpha=self.count)
+
+    def tick(self):
+        """Host side of a step."""
+        self.n += 1
+        if self.active and self.n % self.every == 0:
+            self.reduce()
+
+    def reduce(self):
+        if not self.active:
+            return
+        cur = torch.cuda.current_stream(self.ctx.dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            self.out[0:1].copy_(self.acc)
+            self.out[1].fill_(self.n * self.count)
+            self.ctx.tdist.all_reduce(self.out)
+            self.done.record(self.comm)
+        self.collectives += 1
+
+    def finish(self):
+        if self.active:
+            if self.n % self.every != 0:
+                self.reduce()
+            torch.cuda.current_stream(self.ctx.dev).wait_event(self.done)
+
+
+def measure(ctx, st, K, W, use_graph, min_seconds, want_clocks=False, reduce_every=10):
+    """W warm-up steps, then blocks of exactly K steps (barrier + synchronize on both sides, CUDA events on the launching
+    stream, max over ranks per block) until min_seconds are covered; the median block is reported."""
+    from dmhomo_b200 import _lib
+
+    dev, stream = ctx.dev, ctx.stream
+    n_sets = len(st.sets) if hasattr(st, "sets") else 1
+    graphs, g_loss, g_events = [], [], []
+    reducer = LossReducer(ctx, getattr(st, "B", 1), reduce_every) if st.has_loss else None
     with torch.cuda.stream(stream):
-        # eager warm-up (also what CUDA-graph capture needs before it)
-        for i in range(3):
-            step_eager(i % N_SETS)
+        for i in range(3):                      # eager warm-up (also what CUDA-graph capture needs before it)
+            st.zero_grads()
+            st.step(i % n_sets)
         stream.synchronize()
         n0 = _lib.launch_count()
-        step_eager(0)
+        st.zero_grads()
+        st.step(0)
         stream.synchronize()
         launches_per_step = _lib.launch_count() - n0
-        use_graph = not args.no_graph
+        use_graph = use_graph and st.graphable
         if use_graph:
             try:
                 pool = None
-                for k in range(N_SETS):
+                for k in range(n_sets):
                     st.zero_grads()
                     g = torch.cuda.CUDAGraph()
-                    evs = (torch.cuda.Event(enable_timing=True, external=True),
-                           torch.cuda.Event(enable_timing=True, external=True))
+                    evs = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
                     with torch.cuda.graph(g, pool=pool, stream=stream):
-                        loss = st.forward_backward(k, evs)
+                        loss = st.step(k, evs)
+                        if reducer is not None and loss is not None:
+                            reducer.accumulate(loss)
                     pool = g.pool()
                     graphs.append(g)
                     g_loss.append(loss)
                     g_events.append(evs)
-            except Exception as e:  # capture unsupported here: fall back to eager launches (still our kernels)
-                if rank == 0:
+            except Exception as e:  # capture unsupported here: eager launches (still our kernels)
+                if ctx.rank == 0:
                     import traceback
                     print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
                     traceback.print_exc()
                 graphs, g_loss, g_events, use_graph = [], [], [], False
                 torch.cuda.synchronize()
 
-        def run_step(i, timed_events=None):
-            k = i % N_SETS
-            if use_graph:
-                if dist_step:
-                    stream.wait_event(comm_done[k])   # the previous collective on this set's loss scalar has read it
-                graphs[k].replay()
-                if dist_step:
-                    reduce_loss(g_loss[k], k)
-                return g_loss[k]
-            return step_eager(k, timed_events)
+        eager_evs = []
 
-        # ---- device-resident timed region -------------------------------------------------------
+        def run_step(i, timed=False):
+            k = i % n_sets
+            if use_graph:
+                graphs[k].replay()
+                loss = g_loss[k]
+            else:
+                st.zero_grads()
+                evs = None
+                if timed:
+                    evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    eager_evs.append(evs)
+                loss = st.step(k, evs)
+                if reducer is not None and loss is not None:
+                    reducer.accumulate(loss)
+            if reducer is not None and loss is not None:
+                reducer.tick()
+            return loss
+
         for i in range(W):
             run_step(i)
+        if reducer is not None:
+            reducer.finish()
         stream.synchronize()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
+        sampler = ClockSampler(ctx.local_rank) if (want_clocks and ctx.rank == 0) else None
+        if sampler:
             sampler.start()
             time.sleep(0.25)
-        # barrier + synchronize immediately before the timed region: every rank starts together
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kern_ms, eager_evs = [], []
-        t_wall0 = time.time()
-        e0.record(stream)
-        for i in range(K):
-            if use_graph:
-                run_step(i)
-                # external events are re-recorded by every replay: read them lazily, one replay per set
-            else:
-                evs = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                run_step(i, evs)
-                eager_evs.append(evs)
-        if dist_step:
-            for ev in comm_done:          # the timed region ends when the last collective has finished, too
-                stream.wait_event(ev)
-        e1.record(stream)
-        stream.synchronize()
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
+        blocks, t_wall0 = [], time.time()
+        n_blocks = None
+        while True:
+            ctx.barrier()                        # barrier + synchronize: every rank starts the block together
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                run_step(i, timed=True)
+            if reducer is not None:
+                reducer.finish()                 # the block ends when its last collective has finished, too
+            e1.record(stream)
+            stream.synchronize()
+            ctx.barrier()
+            (ms,) = ctx.max_over_ranks([e0.elapsed_time(e1)])
+            blocks.append(ms)
+            if n_blocks is None:                 # same count on every rank: derived from the max-reduced first block
+                n_blocks = max(1, min(25, int(math.ceil(min_seconds * 1e3 / max(ms, 1e-3)))))
+            if len(blocks) >= n_blocks:
+                break
         t_wall1 = time.time()
-        ms_total = e0.elapsed_time(e1)
         if use_graph:
-            # the last replay of each set left its pair of events recorded inside the timed region
-            for k in range(min(N_SETS, K)):
+            kern = []
+            for k in range(min(n_sets, K)):      # the last replay of each set left its pair of events recorded
                 try:
-                    kern_ms.append(g_events[k][0].elapsed_time(g_events[k][1]))
+                    kern.append(g_events[k][0].elapsed_time(g_events[k][1]))
                 except Exception:
                     pass
         else:
-            kern_ms = [a.elapsed_time(b) for a, b in eager_evs]
-        if rank == 0:
+            kern = [a.elapsed_time(b) for a, b in eager_evs[-max(1, min(len(eager_evs), 4 * K)):]]
+        if sampler:
             time.sleep(0.15)
             sampler.stop()
-        clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
-        final_loss = float(run_step(0).detach())
+        clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+        final = run_step(0)
+        final_loss = float(final.detach()) if final is not None else None
+        stream.synchronize()
+    (kern_ms,) = ctx.max_over_ranks([statistics.median(kern) if kern else 0.0])
+    ms_block = statistics.median(blocks)
+    return dict(ms_block=ms_block, ms_per_step=ms_block / K, blocks=len(blocks), kernel_ms=kern_ms, launches_per_step=int(launches_per_step),
+                clocks=clocks, loss=final_loss, graph=use_graph, run_step=run_step, graphs=graphs, g_loss=g_loss,
+                collectives=(reducer.collectives if reducer else 0))
 
-        # ---- end-to-end: host buffers in, loss out, every step ---------------------------------------
-        B, C, h, w = st.B, st.C, st.h, st.w
-        host = []
-        for k in range(N_SETS):
-            host.append(tuple(t.detach().cpu().pin_memory() for t in st.sets[k]))
-        loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in host[0])
-        Ke = max(3, min(K, 20))
 
-        # Double-buffered like a prefetching loader: the copy of step i + 1 (second stream) runs while step i computes;
-        # every step still pays its own host->device copy and its own loss read-back + synchronize.  The input set a
-        # copy overwrites was last read three steps earlier, and every step ends with a stream synchronize.
-        copy_stream = torch.cuda.Stream(dev)
-        copy_done = [torch.cuda.Event() for _ in range(N_SETS)]
+def sub_result(ctx, st, m, K, scaling, desc, kernel_pixels=None, traffic_key=None, extra=None):
+    px_all = st.pixels * ctx.world
+    r = {"workload": desc, "value": px_all / (m["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": K,
+         "blocks": m["blocks"], "scaling": scaling, "n_gpus": ctx.world, "launch": "CUDA graph replay" if m["graph"] else "eager",
+         "gpu_launches_per_step": m["launches_per_step"], "kernel": st.kernel_label(), "kernel_ms": m["kernel_ms"],
+         "roofline": roofline(ctx, st.bytes_per_px, kernel_pixels or st.pixels, m["kernel_ms"], st.kernel_label(), traffic_key)}
+    if m["loss"] is not None:
+        r["loss"] = m["loss"]
+    if extra:
+        r.update(extra)
+    return r
 
-        def issue_copy(i):
-            k = i % N_SETS
-            with torch.cuda.stream(copy_stream), torch.no_grad():
-                for dst, src in zip(st.sets[k], host[k]):
-                    dst.copy_(src, non_blocking=True)
-                copy_done[k].record(copy_stream)
 
-        def e2e_run(n):
-            issue_copy(0)
-            last = None
-            for i in range(n):
-                if i + 1 < n:
-                    issue_copy(i + 1)
-                stream.wait_event(copy_done[i % N_SETS])
-                loss = run_step(i)
-                loss_host.copy_(loss.detach(), non_blocking=True)
-                stream.synchronize()
-                last = float(loss_host)
-            copy_stream.synchronize()
-            return last
+def free_cuda():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
-        e2e_run(2)
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_run(Ke)
-        torch.cuda.synchronize()
-        if world > 1:
-            tdist.barrier()
-        e2e_s = time.perf_counter() - t0
 
-    # ---- reduce over ranks: max time --------------------------------------------------------------
-    times = torch.tensor([ms_total, e2e_s * 1e3, (sum(kern_ms) / len(kern_ms)) if kern_ms else 0.0], device=dev,
-                         dtype=torch.float64)
-    if world > 1:
-        tdist.all_reduce(times, op=tdist.ReduceOp.MAX)
-    ms_total, e2e_ms, kern_avg_ms = [float(x) for x in times.tolist()]
+def run_side_configs(ctx, args, names):
+    """The other BASELINE configs, each measured the same way as the headline (shorter)."""
+    out = {}
+    K, W = max(3, min(args.steps, 20)), max(args.warmup, 3)
+    graph = not args.no_graph
+    for name in names:
+        try:
+            if name == "cfg1":
+                st = EvalStep(ctx, WORKLOADS["cfg1"]["B"])
+                m = measure(ctx, st, K, W, graph, 0.2)
+                out[name] = sub_result(ctx, st, m, K, "weak", WORKLOADS["cfg1"]["desc"], traffic_key="cfg1")
+            elif name in ("cfg2_direct", "cfg2_dropin"):
+                direct = name == "cfg2_direct"
+                st = PairStep(ctx, "cfg2", WORKLOADS["cfg2"]["B"], variant="direct", api="fused" if direct else "dropin")
+                m = measure(ctx, st, K, W, graph, 0.2)
+                what = ("cfg2, 'direct' variant: warp by the 8-basis flow itself (HEM/model/net.py:808-818), basis_combine + fused warp/mask/L1 with an explicit flow, fwd+bwd"
+                        if direct else
+                        "cfg2, drop-in arm: the reference's own call sequence through compat.* (get_warp_flow x2, create_border_mask x2, LossL1 x2, autograd backward); inline torch of the reference stays torch")
+                out[name] = sub_result(ctx, st, m, K, "weak", what, traffic_key=name)
+            elif name == "cfg3":
+                st = RenderStep(ctx, WORKLOADS["cfg3"]["B"])
+                m = measure(ctx, st, K, W, graph, 0.2)
+                out[name] = sub_result(ctx, st, m, K, "weak", WORKLOADS["cfg3"]["desc"], traffic_key="cfg3",
+                                       extra={"us_per_batch": m["ms_per_step"] * 1e3})
+                out[name]["kernels"] = time_render_ops(ctx, st)
+            elif name == "cfg4":
+                wl = WORKLOADS["cfg4"]
+                extra = {}
+                K4, W4 = max(3, min(args.steps, 6)), 3
+                if ctx.world > 1:
+                    # strong scaling: the whole 4096-pair job on rank 0 alone first (T1), then sharded (TN)
+                    t1 = None
+                    if ctx.rank == 0:
+                        solo = Ctx.__new__(Ctx)
+                        solo.__dict__.update(ctx.__dict__)
+                        solo.world = 1
+                        st1 = PairStep(solo, "cfg4", wl["B"])
+                        t1 = measure(solo, st1, K4, W4, False, 0.0)["ms_per_step"]
+                        del st1
+                        free_cuda()
+                    (t1,) = ctx.max_over_ranks([t1 or 0.0])
+                    extra["t1_ms_per_step"] = t1
+                st = PairStep(ctx, "cfg4", wl["B"] // ctx.world)
+                m = measure(ctx, st, K4, W4, False, 0.2, reduce_every=args.reduce_every)
+                if ctx.world > 1:
+                    extra["strong_scaling_efficiency"] = extra["t1_ms_per_step"] / (ctx.world * m["ms_per_step"])
+                extra["per_gpu_batch"] = wl["B"] // ctx.world
+                extra["loss_allreduces_in_timed_region"] = m["collectives"]
+                out[name] = sub_result(ctx, st, m, K4, "strong", wl["desc"], traffic_key="cfg4", extra=extra)
+            elif name == "cfg5":
+                wl = WORKLOADS["cfg5"]
+                extra = {}
+                K5, W5 = max(3, min(args.steps, 5)), 3
+                if ctx.world > 1:
+                    t1 = None
+                    if ctx.rank == 0:
+                        solo = Ctx.__new__(Ctx)
+                        solo.__dict__.update(ctx.__dict__)
+                        solo.world = 1
+                        st1 = FrameStep(solo, wl["B"])
+                        t1 = measure(solo, st1, 3, 2, False, 0.0)["ms_per_step"]
+                        del st1
+                        free_cuda()
+                    (t1,) = ctx.max_over_ranks([t1 or 0.0])
+                    extra["t1_ms_per_step"] = t1
+                st = FrameStep(ctx, wl["B"] // ctx.world)
+                m = measure(ctx, st, K5, W5, False, 0.2)
+                if ctx.world > 1:
+                    extra["strong_scaling_efficiency"] = extra["t1_ms_per_step"] / (ctx.world * m["ms_per_step"])
+                extra["frames_per_gpu"] = wl["B"] // ctx.world
+                extra["resident_chunk_frames"] = st.chunk
+                out[name] = sub_result(ctx, st, m, K5, "strong", wl["desc"], kernel_pixels=st.kernel_pixels(), traffic_key="cfg5", extra=extra)
+            else:
+                continue
+            del st
+            free_cuda()
+        except Exception as e:  # a side config must never take the headline line down
+            import traceback
+            if ctx.rank == 0:
+                traceback.print_exc()
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+            free_cuda()
+    return out
 
-    if rank == 0:
-        px_step_all = st.pixels * world
-        value = px_step_all * K / (ms_total * 1e-3) / 1e9
-        e2e_val = px_step_all * Ke / (e2e_ms * 1e-3) / 1e9
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.isfile(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload)
-            except Exception:
-                traffic = None
-        roofline = None
-        if kern_avg_ms > 0:
-            alg_bytes = wl["bytes_per_px"] * st.pixels
-            achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "%s<S1,HOMOGRAPHY,FUSED,C=%d,MASKED_DIFF,dense> (both directions, one launch)" % (st.kernel_name, st.C),
-                        "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+
+def time_render_ops(ctx, st):
+    """cfg3: every launch of the rendering batch on its own (CUDA events, rotating input sets)."""
+    res = []
+    with torch.cuda.stream(ctx.stream), torch.no_grad():
+        n_sets = len(st.sets)
+        lists = [st.ops_list(k) for k in range(n_sets)]
+        for idx in range(len(lists[0])):
+            for k in range(n_sets):                 # inputs of this op for every set (and a warm-up of the op itself)
+                for j in range(idx + 1):
+                    lists[k][j][1]()
+            ctx.stream.synchronize()
+            reps = 5 * n_sets
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ctx.stream)
+            for r in range(reps):
+                lists[r % n_sets][idx][1]()
+            e1.record(ctx.stream)
+            ctx.stream.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            label, _, bpp = lists[0][idx]
+            gbs = bpp * st.pixels / (us * 1e-6) / 1e9
+            res.append({"op": label, "us": us, "bytes_per_px": bpp, "achieved_gbs": gbs, "frac": gbs / ctx.peak})
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end: host buffers in, loss out, every step
+# ------------------------------------------------------------------------------------------------
+def run_e2e(ctx, st, m, K):
+    """Three host formats of the same cfg2 step, each copied from pinned host memory inside the timed region (double-
+    buffered on a second stream like a prefetching loader) and with the loss read back + synchronised every step:
+      u8_gray_patches   (2,B,h,w) uint8 grey patches, expanded to fp32 on the GPU (dmh_u8_to_f32)          [headline]
+      u8_rgb_pairs      the on-disk pair format (B,6,360,640) uint8 + crop origins, normalised / greyed / cropped on
+                        the GPU (dmh_pairs_u8_to_gray; HEM/dataset/data_loader.py:121-146)
+      fp32_gray_patches (2,B,1,h,w) fp32, what round 1 shipped"""
+    from dmhomo_b200 import ops
+
+    dev, stream = ctx.dev, ctx.stream
+    B, C, h, w = st.B, st.C, st.h, st.w
+    n_sets = len(st.sets)
+    Ke = max(3, min(K, 20))
+    run_step = m["run_step"]
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    copy_done = [torch.cuda.Event() for _ in range(n_sets)]
+    gen = torch.Generator().manual_seed(1234 + ctx.rank)
+    results = {}
+    with torch.cuda.stream(stream):
+        par_host = [tuple(t.detach().cpu().pin_memory() for t in st.sets[k][2:]) for k in range(n_sets)]
+        formats = ["u8_gray_patches", "fp32_gray_patches"]
+        if C == 1 and h <= 360 and w <= 640:
+            formats.insert(1, "u8_rgb_pairs")
+        for fmt in formats:
+            host, staging = [], []
+            if fmt == "fp32_gray_patches":
+                host = [st.pairs[k].detach().cpu().pin_memory() for k in range(n_sets)]
+                staging = [None] * n_sets
+            elif fmt == "u8_gray_patches":
+                host = [torch.randint(0, 256, (2, B, C, h, w), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_sets)]
+                staging = [torch.empty(2, B, C, h, w, device=dev, dtype=torch.uint8) for _ in range(n_sets)]
+            else:
+                host = [(torch.randint(0, 256, (B, 6, 360, 640), dtype=torch.uint8, generator=gen).pin_memory(),
+                         torch.stack([torch.randint(0, 640 - w + 1, (B,), generator=gen), torch.randint(0, 360 - h + 1, (B,), generator=gen)], 1).int().pin_memory())
+                        for _ in range(n_sets)]
+                staging = [(torch.empty(B, 6, 360, 640, device=dev, dtype=torch.uint8), torch.empty(B, 2, device=dev, dtype=torch.int32))
+                           for _ in range(n_sets)]
+            if fmt == "fp32_gray_patches":
+                h2d = host[0].numel() * 4
+            elif fmt == "u8_gray_patches":
+                h2d = host[0].numel()
+            else:
+                h2d = host[0][0].numel() + host[0][1].numel() * 4
+            h2d += sum(t.numel() * t.element_size() for t in par_host[0])
+
+            def issue_copy(i):
+                k = i % n_sets
+                with torch.cuda.stream(copy_stream), torch.no_grad():
+                    if fmt == "fp32_gray_patches":
+                        st.pairs[k].copy_(host[k], non_blocking=True)
+                    elif fmt == "u8_gray_patches":
+                        staging[k].copy_(host[k], non_blocking=True)
+                    else:
+                        staging[k][0].copy_(host[k][0], non_blocking=True)
+                        staging[k][1].copy_(host[k][1], non_blocking=True)
+                    for dst, src in zip(st.sets[k][2:], par_host[k]):
+                        dst.copy_(src, non_blocking=True)
+                    copy_done[k].record(copy_stream)
+
+            def expand(k):
+                with torch.no_grad():
+                    if fmt == "u8_gray_patches":
+                        ops.u8_to_f32(staging[k], 1.0 / 255.0, 0.0, out=st.pairs[k])
+                    elif fmt == "u8_rgb_pairs":
+                        ops.pairs_u8_to_gray(staging[k][0], start=staging[k][1], patch_size=(h, w), want_rgb=False, want_full=False,
+                                             patch_planar=True, patch_out=st.pairs[k])
+
+            def e2e_loop(n):
+                issue_copy(0)
+                last = None
+                for i in range(n):
+                    if i + 1 < n:
+                        issue_copy(i + 1)         # the copy of step i + 1 overlaps step i
+                    stream.wait_event(copy_done[i % n_sets])
+                    expand(i % n_sets)
+                    loss = run_step(i)
+                    loss_host.copy_(loss.detach(), non_blocking=True)
+                    stream.synchronize()
+                    last = float(loss_host)
+                copy_stream.synchronize()
+                return last
+
+            e2e_loop(2)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            e2e_loop(Ke)
+            torch.cuda.synchronize()
+            ctx.barrier()
+            (sec,) = ctx.max_over_ranks([time.perf_counter() - t0])
+            results[fmt] = {"value": st.pixels * ctx.world * Ke / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                            "d2h_bytes_per_step": 4, "steps": Ke}
+            del host, staging
+    return results
+
+
+def run_ours(args):
+    from dmhomo_b200 import _lib
+
+    ctx = Ctx(args)
+    numa = bind_to_gpu_numa(ctx.local_rank)
+    if args.tuning:
+        _lib.set_tuning(**{k: int(v) for k, _, v in (kv.partition("=") for kv in args.tuning.split(",") if kv)})
+    wl = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+    strong = wl["scaling"] == "strong"
+    per_gpu = wl["B"] // ctx.world if strong else wl["B"]
+    graph = not args.no_graph
+    if args.workload in ("cfg2", "cfg4"):
+        st = PairStep(ctx, args.workload, per_gpu, variant=args.variant, api=args.api)
+        graph = graph and args.workload == "cfg2"
+    elif args.workload == "cfg1":
+        st = EvalStep(ctx, per_gpu)
+    else:
+        st = FrameStep(ctx, per_gpu)
+        graph = False
+    m = measure(ctx, st, K, W, graph, args.min_seconds, want_clocks=True, reduce_every=args.reduce_every)
+    e2e_all = None
+    if not args.no_e2e and args.workload == "cfg2" and args.api == "fused":
+        e2e_all = run_e2e(ctx, st, m, K)
+    kernel_pixels = st.kernel_pixels() if hasattr(st, "kernel_pixels") else st.pixels
+    traffic_key = args.workload if (args.variant == "dlt" and args.api == "fused") else f"{args.workload}_{args.variant if args.api == 'fused' else 'dropin'}"
+    roof = roofline(ctx, st.bytes_per_px, kernel_pixels, m["kernel_ms"], st.kernel_label(), traffic_key)
+    headline_label, launches = st.kernel_label(), m["launches_per_step"]
+    final_loss, used_graph, blocks, ms_per_step, collectives, clocks = m["loss"], m["graph"], m["blocks"], m["ms_per_step"], m["collectives"], m["clocks"]
+    del m
+    del st
+    free_cuda()
+
+    names = [n for n in args.configs.split(",") if n and n != "none"]
+    configs = run_side_configs(ctx, args, names) if names else {}
+
+    if ctx.rank == 0:
+        px_step_all = per_gpu * 2 * wl["h"] * wl["w"] * ctx.world if args.workload != "cfg5" else per_gpu * wl["h"] * wl["w"] * ctx.world
+        value = px_step_all / (ms_per_step * 1e-3) / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if ctx.world == 1 and not args.no_cpu_baseline and args.workload in ("cfg1", "cfg2", "cfg4"):
+            if numa and numa.get("previous"):
+                os.sched_setaffinity(0, numa["previous"])       # the CPU leg uses every host core
             torch.set_num_threads(os.cpu_count() or 1)
             fn, px, what = cpu_step_fn(args.workload, args.cpu_sample)
-            fn()
-            best = None
-            t_budget = time.perf_counter()
-            reps = 0
-            while reps < 3 or (time.perf_counter() - t_budget < 10.0 and reps < 50):   # ~10 s of CPU work, at least 3 passes
-                t0 = time.perf_counter()
-                fn()
-                dt = time.perf_counter() - t0
-                best = dt if best is None else min(best, dt)
-                reps += 1
-                if time.perf_counter() - t_budget > 30:
-                    break
-            cpu = {"value": px / best / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": what + f", best of {reps} passes"}
+            med, reps = time_cpu(fn)
+            cpu = {"value": px / med / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": what + f", median of {reps} passes"}
+        if e2e_all:
+            e2e = dict(e2e_all["u8_gray_patches"])
+            e2e["format"] = "uint8 grey patches (2,B,h,w) in pinned host memory, expanded to fp32 on the GPU"
+            e2e["pipeline"] = "copy of step i+1 on a second stream overlaps step i; loss read back and synchronised every step"
+            e2e["variants"] = e2e_all
+        else:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "not measured for this workload / flags"}
+        cfgd = static_config(args, args.workload, ctx.world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "per_gpu_batch": st.B, "global_batch": st.B * world,
-                       "parallelism": f"batch-sharded x{world}", "param": wl["param"],
-                       "l2": f"{N_SETS} rotating input sets ({N_SETS * 2 * st.B * st.C * st.h * st.w * 4 / 1e6:.0f} MB) > 126 MB L2",
-                       "launch": "CUDA graph replay" if use_graph else "eager", "loss": final_loss,
-                       "api": ("ops.basis_warp_loss" if (args.workload == "cfg2" and args.one_op) else "ops.basis_homography + ops.warp_loss" if args.workload == "cfg2" else "ops.dlt4 + ops.warp_loss")},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": Ke,
-                    "pipeline": "copy of step i+1 on a second stream overlaps step i; loss read back and synchronised every step"},
-            "gpu_launches": int(launches_per_step) * K, "clocks": clocks,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "run": {"launch": "CUDA graph replay" if used_graph else "eager", "loss": final_loss, "blocks_of_K_steps": blocks,
+                    "statistic": "median block, max over ranks per block",
+                    "numa": ({"node": numa["node"], "cpus": numa["cpus"]} if numa else None),
+                    "loss_allreduce": (f"device-accumulated, NCCL all-reduce every {args.reduce_every} steps and at the end of each block ({collectives} collectives)"
+                                       if ctx.world > 1 else "single rank: none")},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches) * K, "clocks": clocks, "configs": configs,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        tdist.barrier()
-        tdist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.tdist.barrier()
+        ctx.tdist.destroy_process_group()
 
 
 def main():

@@ -97,7 +97,9 @@ SIGNATURES = {
     "dmh_warp_perspective": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_eval_point_error": [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_to_homography_ls": [_fp, _fp, _fp, _i, _i, _i, _fp],
-    "dmh_pairs_u8_to_gray": [_fp, _fp, _fp, _fp, _fp, C.POINTER(_d), C.POINTER(_d), _i, _i, _i, _i, _i, _fp],
+    "dmh_pairs_u8_to_gray": [_fp, _fp, _fp, _fp, _fp, C.POINTER(_d), C.POINTER(_d), _i, _i, _i, _i, _i, _i, _fp],
+    "dmh_u8_to_f32": [_fp, _fp, _i64, _f, _f, _fp],
+    "dmh_grid_normalize": [_fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_upsample": [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_flow_upsample_backward": [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
 }

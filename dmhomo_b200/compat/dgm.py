@@ -7,7 +7,7 @@ import torch
 from .. import ops
 
 __all__ = ["mesh_grid", "norm_grid", "flow_warp", "homo_to_flow", "adapt_homography_to_preprocessing_v3",
-           "flow_to_image", "visulize_flow", "postProcess", "postProcess_cv2", "homo_gen", "photo_loss"]
+           "flow_to_image", "visulize_flow", "postProcess", "postProcess_cv2", "homo_gen", "photo_loss", "resize_flow"]
 
 
 def mesh_grid(B, H, W):
@@ -96,3 +96,11 @@ def photo_loss(im1, im2, flow, mask, alpha_bar_t, fused=True):
     term = ops.WarpTerm(im2, im1, flow, soft_mask=mask, sample_weight=alpha_bar_t.reshape(-1))
     return ops.warp_loss([term], kind=ops.PARAM_FLOW, sampler=ops.S3_BORDER, loss_form=ops.LOSS_DIFF_MASKED,
                          border_mask=False, fused=fused)
+
+
+def resize_flow(flow, size):
+    """ddpm.py:1249-1259: cv2.resize (bilinear, half-pixel centres) of an (h,w,2) numpy flow to (size,size,2) with the
+    two channels scaled by size / w and size / h."""
+    f = torch.as_tensor(np.ascontiguousarray(flow, dtype=np.float32), device="cuda").permute(2, 0, 1).unsqueeze(0)
+    out = ops.flow_upsample(f.contiguous(), (int(size), int(size)), if_rate=True, align_corners=False)
+    return out[0].permute(1, 2, 0).contiguous().cpu().numpy()

@@ -7,7 +7,8 @@ import torch
 from .. import ops
 
 __all__ = ["get_gt_correspondence_mask", "create_border_mask", "define_mask_zero_borders", "convert_flow_to_mapping",
-           "convert_mapping_to_flow", "from_homography_to_pixel_wise_mapping"]
+           "convert_mapping_to_flow", "from_homography_to_pixel_wise_mapping", "normalize", "unnormalize",
+           "unormalise_flow_or_mapping", "unormalise_and_convert_mapping_to_flow"]
 
 
 def _bchw(flow):
@@ -91,3 +92,39 @@ def from_homography_to_pixel_wise_mapping(shape, H):
     Ht = torch.as_tensor(np.asarray(H, dtype=np.float64).reshape(1, 3, 3), device="cuda")
     m = ops.homography_to_flow_f64(Ht, h, w, eps=1e-8, channels_last=False, as_mapping=True)[0].cpu().numpy()
     return m[0], m[1]
+
+
+def _grid_op(t, mode, output_channel_first):
+    """Layout handling of the reference's torch branches (...operations.py:227-451): 3-D or 4-D, channel-first or
+    channel-last in, channel-first or channel-last out; numpy inputs are moved to the GPU and come back as numpy."""
+    is_np = isinstance(t, np.ndarray)
+    x = torch.from_numpy(np.ascontiguousarray(t)).cuda() if is_np else t
+    squeeze = x.dim() == 3
+    f = x.unsqueeze(0) if squeeze else x
+    if f.shape[1] != 2:
+        f = f.permute(0, 3, 1, 2)
+    out = ops.grid_normalize(f, mode)
+    if not output_channel_first:
+        out = out.permute(0, 2, 3, 1)
+    out = out[0] if squeeze else out
+    return out.cpu().numpy().astype(np.float32) if is_np else out
+
+
+def normalize(tensor, output_channel_first=True):
+    """...operations.py:419-451: pixel coordinates -> [-1, 1] (2*t/(S-1) - 1)."""
+    return _grid_op(tensor, 0, output_channel_first)
+
+
+def unnormalize(tensor, output_channel_first=True):
+    """...operations.py:384-416: [-1, 1] -> pixel coordinates ((t+1)*(S-1)/2)."""
+    return _grid_op(tensor, 1, output_channel_first)
+
+
+def unormalise_flow_or_mapping(map, output_channel_first=True):
+    """...operations.py:318-381."""
+    return _grid_op(map, 1, output_channel_first)
+
+
+def unormalise_and_convert_mapping_to_flow(map, output_channel_first=True):
+    """...operations.py:227-315: un-normalise a [-1, 1] mapping and subtract the pixel grid."""
+    return _grid_op(map, 2, output_channel_first)

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-__all__ = ["DLT", "WarpMat", "RescaleH", "Transform", "WarpImages", "get_grid", "get_src_p", "get_point_pairs",
+__all__ = ["DLT", "WarpMat", "RescaleH", "Transform", "WarpImages", "CropPatchFromFull", "get_grid", "get_src_p", "get_point_pairs",
            "DLT_solve", "get_flow", "transformer", "get_warp_flow", "upsample2d_flow_as", "gen_basis"]
 
 
@@ -69,6 +69,23 @@ def Transform(H, input_map, start, patch_size, start_zero=False):
     if start_zero:
         start = torch.zeros_like(start)
     return WarpImages(input_map, H, start, patch_size)
+
+
+def CropPatchFromFull(patch_size, full_img, start, rescale=False):
+    """HEM/model/utils.py:200-291.  patch_size = (w, h); start (B,1,2) = per-sample (x, y) origin.
+    rescale=True: bilinear interpolation at grid + start with the coordinate clamped to the image first - exactly the
+    S1B sampler under an identity homography (one kernel).  rescale=False: an integer gather of the window (pure data
+    movement, one torch indexing op)."""
+    pw, ph = patch_size
+    B, C, H, W = full_img.shape
+    st = start.reshape(B, 2)
+    if rescale:
+        eye = torch.eye(3, device=full_img.device, dtype=torch.float32).repeat(B, 1, 1)
+        return ops.warp(full_img, eye, kind=ops.PARAM_HOMOGRAPHY, sampler=ops.S1B, out_hw=(ph, pw), start=st.float())
+    xs = st[:, 0].long().view(B, 1, 1) + torch.arange(pw, device=full_img.device).view(1, 1, pw)
+    ys = st[:, 1].long().view(B, 1, 1) + torch.arange(ph, device=full_img.device).view(1, ph, 1)
+    idx = (ys * W + xs).view(B, 1, ph * pw).expand(B, C, ph * pw)
+    return torch.gather(full_img.reshape(B, C, H * W), 2, idx).view(B, C, ph, pw).contiguous()
 
 
 def get_grid(batch_size, H, W, start=0):

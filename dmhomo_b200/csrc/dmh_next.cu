@@ -28,7 +28,7 @@ struct PairNorm {
 __global__ void __launch_bounds__(kThreads) pairs_u8_kernel(const uint8_t* __restrict__ img12, const int* __restrict__ start,
                                                             float* __restrict__ grey_full, float* __restrict__ grey_patch,
                                                             float* __restrict__ rgb_full, const __grid_constant__ PairNorm nm,
-                                                            int B, int H, int W, int ph, int pw) {
+                                                            int B, int H, int W, int ph, int pw, int planar) {
   __shared__ double lut[3][256];
   __shared__ float lut255[256];
   for (int t = threadIdx.x; t < 768; t += blockDim.x) {
@@ -69,14 +69,16 @@ __global__ void __launch_bounds__(kThreads) pairs_u8_kernel(const uint8_t* __res
       const int x0 = __ldg(start + 2 * b), y0 = __ldg(start + 2 * b + 1);
       const int py = y - y0;
       if (py >= 0 && py < ph) {
-        float* o = grey_patch + (size_t)b * 2 * ph * pw + (size_t)py * pw;
+        // (B,2,ph,pw), or planar (2,B,ph,pw): the two images of a pair as two dense batches
+        const size_t pp = (size_t)ph * pw, second = planar ? (size_t)B * pp : pp;
+        float* o = grey_patch + (size_t)b * (planar ? pp : 2 * pp) + (size_t)py * pw;
         const float v1[4] = {g1.x, g1.y, g1.z, g1.w}, v2[4] = {g2.x, g2.y, g2.z, g2.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int px = x + k - x0;
           if (px >= 0 && px < pw) {
             o[px] = v1[k];
-            o[(size_t)ph * pw + px] = v2[k];
+            o[second + px] = v2[k];
           }
         }
       }
@@ -185,12 +187,78 @@ float scale_of(int in, int out, bool align) {
   return (float)in / (float)out;
 }
 
+// dst = fl(fl(float(u8) * scale) + bias): 16 bytes in, 64 bytes out per thread and step
+__global__ void __launch_bounds__(kThreads) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n16,
+                                                             long long n, float scale, float bias) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(dst) + 4 * i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = make_float4(add_rn(mul_rn((float)(wd[k] & 255u), scale), bias), add_rn(mul_rn((float)((wd[k] >> 8) & 255u), scale), bias),
+                         add_rn(mul_rn((float)((wd[k] >> 16) & 255u), scale), bias), add_rn(mul_rn((float)(wd[k] >> 24), scale), bias));
+  }
+  for (long long i = n16 * 16 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = add_rn(mul_rn((float)src[i], scale), bias);
+}
+
+// normalize / unnormalize / unormalise_and_convert_mapping_to_flow (flow_and_mapping_operations.py:227-451), channel-first
+// (B,2,H,W): channel 0 against W, channel 1 against H, every operation rounded separately in the reference's order:
+//   mode 0  normalize    2 * t / (S - 1) - 1
+//   mode 1  unnormalize  (t + 1) * (S - 1) / 2
+//   mode 2  unnormalize, then minus the pixel grid (mapping -> flow)
+__global__ void __launch_bounds__(kThreads) grid_normalize_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H,
+                                                                  int W, int mode) {
+  const unsigned plane = (unsigned)(H * W);
+  const float sw = (float)(W - 1), sh = (float)(H - 1);
+  DMH_PLANE_LOOP(b, p, B, plane) {
+    const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+    const size_t o = (size_t)b * 2 * plane + p;
+    const float u = src[o], v = src[o + plane];
+    float ru, rv;
+    if (mode == 0) {
+      ru = sub_rn(div_rn(mul_rn(2.f, u), sw), 1.f);
+      rv = sub_rn(div_rn(mul_rn(2.f, v), sh), 1.f);
+    } else {
+      ru = div_rn(mul_rn(add_rn(u, 1.f), sw), 2.f);
+      rv = div_rn(mul_rn(add_rn(v, 1.f), sh), 2.f);
+      if (mode == 2) {
+        ru = sub_rn(ru, (float)x);
+        rv = sub_rn(rv, (float)y);
+      }
+    }
+    dst[o] = ru;
+    dst[o + plane] = rv;
+  }
+}
+
 }  // namespace
 }  // namespace dmh
 
+extern "C" int dmh_grid_normalize(const float* src, float* dst, int B, int H, int W, int mode, void* stream) {
+  DMH_REQUIRE(src && dst, "grid_normalize: null pointer");
+  DMH_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < 2147483647LL, "grid_normalize: bad size");
+  DMH_REQUIRE(mode >= 0 && mode <= 2, "grid_normalize: bad mode %d", mode);
+  dmh::grid_normalize_kernel<<<dmh::plane_grid((long long)H * W, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(src, dst, B, H, W, mode);
+  return dmh::launched("grid_normalize_kernel");
+}
+
+extern "C" int dmh_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float scale, float bias, void* stream) {
+  DMH_REQUIRE(src && dst && n > 0, "u8_to_f32: null pointer or empty");
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const long long n16 = vec ? n / 16 : 0;
+  long long blocks = ((vec ? n16 : n) + dmh::kThreads - 1) / dmh::kThreads;
+  if (blocks > dmh::kNumSMs * 16) blocks = dmh::kNumSMs * 16;
+  if (blocks < 1) blocks = 1;
+  dmh::u8_to_f32_kernel<<<(unsigned)blocks, dmh::kThreads, 0, dmh::as_stream(stream)>>>(src, dst, n16, n, scale, bias);
+  return dmh::launched("u8_to_f32_kernel");
+}
+
 extern "C" int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, float* gray_full, float* gray_patch, float* rgb_full,
                                     const double* mean3, const double* std3, int B, int H, int W, int patch_h, int patch_w,
-                                    void* stream) {
+                                    int patch_planar, void* stream) {
   DMH_REQUIRE(img12 && mean3 && std3, "pairs_u8_to_gray: null pointer");
   DMH_REQUIRE(gray_full || gray_patch || rgb_full, "pairs_u8_to_gray: no output requested");
   DMH_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < 2147483647LL, "pairs_u8_to_gray: bad size");
@@ -203,7 +271,7 @@ extern "C" int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, floa
     DMH_REQUIRE(std3[c] != 0.0, "pairs_u8_to_gray: std[%d] is zero", c);
   }
   dmh::pairs_u8_kernel<<<dmh::plane_grid((long long)H * W / 4, B), dmh::kThreads, 0, dmh::as_stream(stream)>>>(img12, start, gray_full, gray_patch,
-                                                                                        rgb_full, nm, B, H, W, patch_h, patch_w);
+                                                                                        rgb_full, nm, B, H, W, patch_h, patch_w, patch_planar);
   return dmh::launched("pairs_u8_kernel");
 }
 

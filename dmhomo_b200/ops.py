@@ -15,7 +15,7 @@ from ._lib import (LOSS_DIFF_MASKED, LOSS_MASKED_DIFF, LOSS_NONE, PARAM_BASIS8, 
 __all__ = [
     "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8",
     "LOSS_NONE", "LOSS_MASKED_DIFF", "LOSS_DIFF_MASKED", "dlt4", "homography_to_flow", "homography_to_flow_f64",
-    "basis_combine", "basis_corner_offsets", "basis_homography", "warp", "warp_loss", "WarpTerm", "border_mask", "zero_border_mask",
+    "basis_combine", "basis_corner_offsets", "basis_homography", "warp", "warp_into", "warp_loss", "warp_eval", "WarpTerm", "u8_to_f32", "pairs_u8_to_gray", "border_mask", "zero_border_mask",
     "l1_loss", "flow_to_rgb", "warp_perspective", "eval_point_error", "flow_to_homography_ls",
 ]
 
@@ -404,6 +404,25 @@ def warp(img, param, kind=PARAM_FLOW, sampler=S1, out_hw=None, start=0, basis=No
     return ret[0] if len(ret) == 1 else tuple(ret)
 
 
+def warp_into(img, param, out, valid=None, kind=PARAM_HOMOGRAPHY, sampler=S1, start=0, basis=None, divide=1):
+    """warp() into caller-owned buffers, no autograd: out (B,C,h,w) fp32 and, optionally, valid (B,h,w) uint8 (the M1
+    mask) are overwritten.  For resident pipelines that reuse their output buffers (frame-sequence warps, cfg 5)."""
+    dev = _cuda(img, param, out, valid, basis)
+    img_c, par_c = _f32(img), _f32(param)
+    B, Cc, _, _ = img_c.shape
+    h, w = out.shape[-2:]
+    if out.dtype != torch.float32 or tuple(out.shape) != (B, Cc, h, w) or not out.is_contiguous():
+        raise ValueError("warp_into: out must be a contiguous fp32 (B,C,h,w) tensor")
+    if valid is not None and (valid.dtype != torch.uint8 or valid.numel() != B * h * w or not valid.is_contiguous()):
+        raise ValueError("warp_into: valid must be a contiguous uint8 (B,h,w) tensor")
+    _param_shape_check(kind, par_c, B, h, w, divide)
+    sx, sy, per = _start_args(start, B, dev)
+    d = _desc(sampler, kind, img_c, par_c, h, w, basis=_f32(basis), start=per, start_x=sx, start_y=sy, divide=divide,
+              out=out, valid=valid)
+    _run_warp([d], dev)
+    return out, valid
+
+
 # ----------------------------------------------------------------------------------------------
 # fused warp + mask + masked-L1 (+ gradients) (A13, A14)
 # ----------------------------------------------------------------------------------------------
@@ -578,6 +597,43 @@ def warp_loss(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DI
     cfg = dict(kind=kind, sampler=sampler, loss_form=loss_form, border_mask=bool(border_mask), weight=float(weight),
                divide=int(divide), start=start, fused=bool(fused))
     return _WarpLoss.apply(cfg, basis, *flat)
+
+
+def warp_eval(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DIFF, border_mask=True, weight=1.0, basis=None,
+              divide=1, start=0, masks_as_bool=True):
+    """Evaluation pass, one launch for all `terms` (e.g. both directions of a pair), no gradients: per term the warped
+    image (get_warp_flow, HEM/model/utils.py:548-553) and the M1 validity mask (get_gt_correspondence_mask,
+    flow_and_mapping_operations.py:45-71), plus the masked-L1 total of warp_loss() (HEM/loss/losses.py:142-146).
+    Returns (loss scalar, [warped (B,C,h,w) per term], [mask (B,h,w) bool (uint8 with masks_as_bool=False) per term])."""
+    if isinstance(terms, WarpTerm):
+        terms = [terms]
+    n = len(terms)
+    dev = _cuda(basis, *[t for tm in terms for t in (tm.src, tm.target, tm.param, tm.soft_mask, tm.sample_weight)])
+    bas_c = _f32(basis)
+    with torch.no_grad():
+        tl = [[_f32(t) for t in (tm.src, tm.target, tm.param, tm.soft_mask, tm.sample_weight)] for tm in terms]
+        B, Cc, Hs, Ws = tl[0][0].shape
+        h, w = tl[0][1].shape[-2:]
+        for src, tgt, par, soft, sw in tl:
+            if tuple(tgt.shape) != (B, Cc, h, w) or src.shape[:2] != (B, Cc):
+                raise ValueError("warp_eval: src (B,C,Hs,Ws) / target (B,C,h,w) shapes disagree")
+            _param_shape_check(kind, par, B, h, w, divide)
+        sx, sy, per = _start_args(start, B, dev)
+        scale = float(weight) / float(B * Cc * h * w)
+        acc = torch.zeros(n * B, device=dev, dtype=torch.float64)
+        outs = [torch.empty(B, Cc, h, w, device=dev, dtype=torch.float32) for _ in range(n)]
+        valids = [torch.empty(B, h, w, device=dev, dtype=torch.uint8) for _ in range(n)]
+        descs = [_desc(sampler, kind, src, par, h, w, basis=bas_c, start=per, start_x=sx, start_y=sy, divide=divide,
+                       target=tgt, soft_mask=soft, sample_weight=sw, use_border_mask=border_mask, loss_form=loss_form,
+                       grad_loss_scale=scale, loss_acc=acc[i * B:(i + 1) * B], out=outs[i], valid=valids[i])
+                 for i, (src, tgt, par, soft, sw) in enumerate(tl)]
+        _run_warp(descs, dev)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        acc_ptrs = (C.c_void_p * n)(*[acc[i * B:(i + 1) * B].data_ptr() for i in range(n)])
+        sw_ptrs = (C.c_void_p * n)(*[_p(t[4]) for t in tl])
+        with torch.cuda.device(dev):
+            L.check(L.lib().dmh_loss_finish(acc_ptrs, sw_ptrs, n, B, scale, _p(loss), _stream(dev)), "loss_finish")
+    return loss, outs, ([v.bool() for v in valids] if masks_as_bool else valids)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -851,16 +907,19 @@ MEAN_I = (118.93, 113.97, 102.60)   # HEM/dataset/data_loader.py:103-104
 STD_I = (69.85, 68.81, 72.45)
 
 
-def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEAN_I, std=STD_I):
+def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEAN_I, std=STD_I, want_full=True,
+                     patch_planar=False, patch_out=None):
     """The on-disk pair format batched as uint8 (B,6,H,W) (CUDA) -> (imgs_gray_full (B,2,H,W), imgs_gray_patch
     (B,2,ph,pw) or None, imgs_rgb_full (B,6,H,W) or None) exactly as DGMTrainData.__getitem__ / data_aug produce them
-    on the host in numpy fp64 (HEM/dataset/data_loader.py:121-146, 217-255).  start: (B,2) int (x, y) crop origins."""
+    on the host in numpy fp64 (HEM/dataset/data_loader.py:121-146, 217-255).  start: (B,2) int (x, y) crop origins.
+    patch_planar: the patch comes back as (2,B,ph,pw) (image 1 / image 2 as two dense batches, what the warp ops
+    take); patch_out: write the patch into this fp32 buffer of the right size."""
     dev = _cuda(img12)
     if img12.dtype != torch.uint8 or img12.dim() != 4 or img12.shape[1] != 6:
         raise ValueError("pairs_u8_to_gray: img12 must be uint8 (B,6,H,W)")
     x = img12.contiguous()
     B, _, H, W = x.shape
-    full = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
+    full = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32) if want_full else None
     rgb = torch.empty(B, 6, H, W, device=dev, dtype=torch.float32) if want_rgb else None
     patch, st, ph, pw = None, None, 0, 0
     if patch_size is not None:
@@ -874,13 +933,51 @@ def pairs_u8_to_gray(img12, start=None, patch_size=None, want_rgb=True, mean=MEA
             if bool(((sh[:, 0] < 0) | (sh[:, 0] + pw > W) | (sh[:, 1] < 0) | (sh[:, 1] + ph > H)).any()):
                 raise ValueError("pairs_u8_to_gray: crop window outside the image")
         st = torch.as_tensor(start, device=dev).to(torch.int32).reshape(B, 2).contiguous()
-        # device-resident origins are not validated on the host: pixels of a window that leaves the image stay 0
-        patch = (torch.zeros if (torch.is_tensor(start) and start.is_cuda) else torch.empty)(B, 2, ph, pw, device=dev, dtype=torch.float32)
+        shape = (2, B, ph, pw) if patch_planar else (B, 2, ph, pw)
+        if patch_out is not None:
+            if patch_out.dtype != torch.float32 or patch_out.numel() != 2 * B * ph * pw or not patch_out.is_contiguous():
+                raise ValueError("pairs_u8_to_gray: patch_out must be a contiguous fp32 buffer of 2*B*ph*pw values")
+            patch = patch_out.view(shape)
+        else:
+            # device-resident origins are not validated on the host: pixels of a window that leaves the image stay 0
+            patch = (torch.zeros if (torch.is_tensor(start) and start.is_cuda) else torch.empty)(shape, device=dev, dtype=torch.float32)
+    if full is None and rgb is None and patch is None:
+        raise ValueError("pairs_u8_to_gray: no output requested")
     m3, s3 = (C.c_double * 3)(*[float(v) for v in mean]), (C.c_double * 3)(*[float(v) for v in std])
     with torch.cuda.device(dev):
         L.check(L.lib().dmh_pairs_u8_to_gray(_p(x), _p(st), _p(full), _p(patch), _p(rgb), m3, s3, B, H, W, ph, pw,
-                                             _stream(dev)), "pairs_u8_to_gray")
+                                             int(bool(patch_planar)), _stream(dev)), "pairs_u8_to_gray")
     return full, patch, rgb
+
+
+def u8_to_f32(src, scale=1.0 / 255.0, bias=0.0, out=None):
+    """float32(u8) * scale + bias (separately rounded): uint8 frames / grey patches shipped over PCIe at one byte per
+    pixel and expanded in HBM (torch.Tensor(img).float() / 255 of the loaders, HEM/dataset/data_loader.py:139-146)."""
+    dev = _cuda(src, out)
+    if src.dtype != torch.uint8:
+        raise ValueError("u8_to_f32: src must be uint8")
+    x = src.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=dev, dtype=torch.float32)
+    elif out.dtype != torch.float32 or out.numel() != x.numel() or not out.is_contiguous():
+        raise ValueError("u8_to_f32: out must be a contiguous fp32 tensor of the same size")
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_u8_to_f32(_p(x), _p(out), x.numel(), float(scale), float(bias), _stream(dev)), "u8_to_f32")
+    return out
+
+
+def grid_normalize(t, mode):
+    """normalize (mode 0) / unnormalize (1) / unnormalize-and-subtract-grid (2) of a channel-first (B,2,H,W) tensor
+    (HEM/utils_operations/flow_and_mapping_operations.py:227-451)."""
+    dev = _cuda(t)
+    x = _f32(t)
+    if x.dim() != 4 or x.shape[1] != 2:
+        raise ValueError("grid_normalize: expected (B,2,H,W)")
+    B, _, H, W = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        L.check(L.lib().dmh_grid_normalize(_p(x), _p(out), B, H, W, int(mode), _stream(dev)), "grid_normalize")
+    return out
 
 
 class _FlowUpsample(torch.autograd.Function):

@@ -137,8 +137,13 @@ DMH_API uint64_t dmh_launch_count(void);
  * bench.py labels its roofline object with it. */
 DMH_API const char* dmh_last_kernel_name(void);
 /* Development knobs, process-wide, read at launch time (defaults = the measured best; none changes a result):
- *   "tile"          0 scalar kernels only | 1 TMA tile kernel for the dense C = 1 launches | 2 also C = 3 (default)
+ *   "tile"          0 scalar kernels only | 1 TMA tile kernel for the dense C = 1 launches | 2 also the gradient-free
+ *                   C = 3 launches (default) | 3 also the C = 3 training launch
  *   "tile_interior" bit 0 interior-tile body, bit 1 mixed-tile body of the tile kernel (default 3)
+ *   "tile_dyn"      percent of a tile launch's tile list handed out dynamically, the rest is split statically
+ *                   (default -1: 15 for the C = 1 training launch, 100 otherwise)
+ *   "tile_chunk"    longest run of tiles per dynamic claim, 1 .. 8; runs shrink to single tiles at the end
+ *                   (default -1: 1 / 4 / 8 for the C = 1 training, C = 3 training and gradient-free launches)
  * The library reads no environment variables.  Unknown key: DMH_EINVAL. */
 DMH_API int dmh_set_tuning(const char* key, int value);
 DMH_API int dmh_get_tuning(const char* key, int* value);
@@ -190,10 +195,18 @@ DMH_API int dmh_homography_to_flow_f64(const double* H, float* out, int B, int h
  * data_aug hand the network (HEM/dataset/data_loader.py:121-146, 217-255): gray_full (B,2,H,W) =
  * float32(mean_c((u8 - mean_c) / std_c)) in fp64 (numpy), gray_patch (B,2,ph,pw) = its crop at start[b] = (x, y)
  * (int32, (B,2)), rgb_full (B,6,H,W) = float32(u8) / 255.  Any output may be null.  W % 4 == 0.
- * mean3 / std3 are HOST pointers to three doubles. */
+ * patch_planar != 0: gray_patch is laid out (2,B,ph,pw) - image 1 and image 2 of every pair as two dense batches,
+ * the form the warp entry points take.  mean3 / std3 are HOST pointers to three doubles. */
 DMH_API int dmh_pairs_u8_to_gray(const uint8_t* img12, const int* start, float* gray_full, float* gray_patch,
                          float* rgb_full, const double* mean3, const double* std3, int B, int H, int W,
-                         int patch_h, int patch_w, void* stream);
+                         int patch_h, int patch_w, int patch_planar, void* stream);
+/* dst[i] = fl(fl(float(src[i]) * scale) + bias), i < n: uint8 frames / grey patches shipped over PCIe at one byte
+ * per pixel and expanded in HBM (the loaders' torch.Tensor(img).float() / 255, HEM/dataset/data_loader.py:139-146). */
+DMH_API int dmh_u8_to_f32(const uint8_t* src, float* dst, int64_t n, float scale, float bias, void* stream);
+/* normalize(tensor) / unnormalize(tensor) / unormalise_and_convert_mapping_to_flow(map)
+ * (HEM/utils_operations/flow_and_mapping_operations.py:419-451, 384-416, 227-315; torch branches): src, dst (B,2,H,W);
+ * mode 0: 2*t/(S-1) - 1; mode 1: (t+1)*(S-1)/2; mode 2: mode 1 minus the pixel grid; S = W for channel 0, H for channel 1. */
+DMH_API int dmh_grid_normalize(const float* src, float* dst, int B, int H, int W, int mode, void* stream);
 /* upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate, align_corners)
  * (HEM/model/utils.py:556-572; swin_multi.py:1175-1182): flow (B,2,hi,wi) -> out (B,2,ho,wo), bilinear with
  * torch's index / lambda rules; if_rate multiplies channel 0 by wo/wi and channel 1 by ho/hi first (the

@@ -129,3 +129,86 @@ def test_pyramid_level_feature_warp(C):
     assert (out_g.detach().cpu() - out_c.detach()).abs().max().item() < 1e-4
     assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4
     assert ((wg.grad.cpu() - wc.grad).norm() / wc.grad.norm()).item() < 1e-3
+
+
+# ---------------------------------------------------------------------------------- remaining helpers of the module files
+def test_normalize_family_bit_exact():
+    from dmhomo_b200.compat import flow_and_mapping_operations as fmo
+
+    gen = torch.Generator().manual_seed(61)
+    pix = torch.rand(3, 2, 37, 52, generator=gen) * 60 - 4
+    nrm = torch.rand(3, 2, 37, 52, generator=gen) * 2.4 - 1.2
+    assert torch.equal(fmo.normalize(pix.to(DEV)).cpu(), port.grid_normalize(pix, 0))
+    assert torch.equal(fmo.unnormalize(nrm.to(DEV)).cpu(), port.grid_normalize(nrm, 1))
+    assert torch.equal(fmo.unormalise_flow_or_mapping(nrm.to(DEV)).cpu(), port.grid_normalize(nrm, 1))
+    assert torch.equal(fmo.unormalise_and_convert_mapping_to_flow(nrm.to(DEV)).cpu(), port.grid_normalize(nrm, 2))
+    # channel-last in / out and 3-D inputs, as the reference accepts them
+    cl = fmo.unnormalize(nrm.permute(0, 2, 3, 1).to(DEV), output_channel_first=False).cpu()
+    assert torch.equal(cl, port.grid_normalize(nrm, 1).permute(0, 2, 3, 1))
+    assert torch.equal(fmo.normalize(pix[0].to(DEV)).cpu(), port.grid_normalize(pix[:1], 0)[0])
+
+
+def test_crop_patch_from_full():
+    gen = torch.Generator().manual_seed(62)
+    img = torch.rand(3, 2, 40, 56, generator=gen)
+    start_i = torch.tensor([[[3, 2]], [[0, 0]], [[20, 12]]])
+    a = hem_utils.CropPatchFromFull((24, 20), img.to(DEV), start_i.to(DEV), rescale=False)
+    assert torch.equal(a.cpu(), port.crop_patch_from_full((24, 20), img, start_i, rescale=False))
+    start_f = torch.tensor([[[3.25, 2.5]], [[-1.5, 0.75]], [[40.5, 27.25]]])
+    b = hem_utils.CropPatchFromFull((24, 20), img.to(DEV), start_f.to(DEV), rescale=True)
+    assert (b.cpu() - port.crop_patch_from_full((24, 20), img, start_f, rescale=True)).abs().max().item() < 1e-6
+
+
+def test_resize_flow_matches_cv2():
+    from dmhomo_b200.compat import dgm
+
+    rs = np.random.default_rng(63)
+    for (h, w, size) in ((36, 64, 24), (45, 80, 128), (360, 640, 256)):
+        fl = rs.standard_normal((h, w, 2)).astype(np.float32) * 5
+        ours = dgm.resize_flow(fl, size)
+        ref = port.resize_flow(fl.copy(), size)
+        assert ours.shape == ref.shape
+        assert np.abs(ours - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------- formats / resident pipelines of bench.py
+def test_u8_to_f32_and_planar_patch():
+    rs = np.random.default_rng(64)
+    u8 = torch.from_numpy(rs.integers(0, 256, size=(2, 3, 1, 40, 52), dtype=np.uint8))
+    out = ops.u8_to_f32(u8.to(DEV), 1.0 / 255.0, 0.0)
+    assert torch.equal(out.cpu(), u8.float() * (1.0 / 255.0))
+    odd = u8.flatten()[:1003]                                   # scalar tail + unaligned length
+    assert torch.equal(ops.u8_to_f32(odd.to(DEV), 0.5, -3.0).cpu(), odd.float() * 0.5 + (-3.0))
+    with pytest.raises(ValueError):
+        ops.u8_to_f32(u8.float().to(DEV))
+    # planar patch layout (2,B,ph,pw) == the (B,2,ph,pw) patch transposed, written into a caller-owned buffer
+    img12 = torch.from_numpy(rs.integers(0, 256, size=(3, 6, 48, 64), dtype=np.uint8)).to(DEV)
+    start = torch.tensor([[7, 11], [0, 0], [24, 24]])
+    _, patch, _ = ops.pairs_u8_to_gray(img12, start=start, patch_size=(24, 40), want_rgb=False)
+    buf = torch.empty(2, 3, 1, 24, 40, device=DEV)
+    full, planar, rgb = ops.pairs_u8_to_gray(img12, start=start.to(DEV), patch_size=(24, 40), want_rgb=False, want_full=False,
+                                            patch_planar=True, patch_out=buf)
+    assert full is None and rgb is None and planar.data_ptr() == buf.data_ptr()
+    assert torch.equal(planar, patch.transpose(0, 1))
+
+
+@pytest.mark.parametrize("C,h,w", [(1, 360, 640), (3, 128, 192), (1, 72, 100)])
+def test_warp_eval_and_warp_into(C, h, w):
+    """The evaluation pass (warped + mask + loss, one launch) and the buffer-reusing forward warp against warp() /
+    warp_loss(); (1, 72, 100) has a width the tile kernel does not take (general kernel)."""
+    B = 4
+    gen = g(65)
+    img1, img2 = torch.rand(B, C, h, w, generator=gen).to(DEV), torch.rand(B, C, h, w, generator=gen).to(DEV)
+    src = port.corner_points(2 * B, h, w)
+    H = port.dlt4(src, src + (torch.rand(2 * B, 4, 2, generator=gen) * 2 - 1) * 12.0).to(DEV)
+    loss, outs, masks = ops.warp_eval([ops.WarpTerm(img2, img1, H[:B]), ops.WarpTerm(img1, img2, H[B:])], kind=ops.PARAM_HOMOGRAPHY)
+    w2, m2 = ops.warp(img2, H[:B], kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
+    w1, m1 = ops.warp(img1, H[B:], kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
+    assert torch.equal(outs[0], w2) and torch.equal(outs[1], w1)
+    assert torch.equal(masks[0], m2) and torch.equal(masks[1], m1)
+    ref = ops.warp_loss([ops.WarpTerm(img2, img1, H[:B]), ops.WarpTerm(img1, img2, H[B:])], kind=ops.PARAM_HOMOGRAPHY, fused=False)
+    assert abs(loss.item() - ref.item()) < 1e-6
+    out = torch.full_like(img2, -7.0)
+    valid = torch.full((B, h, w), 9, dtype=torch.uint8, device=DEV)
+    ops.warp_into(img2, H[:B], out, valid, kind=ops.PARAM_HOMOGRAPHY)
+    assert torch.equal(out, w2) and torch.equal(valid.bool(), m2)

@@ -4,7 +4,7 @@ The dense S1 homography launches (forward: warped image + validity mask; fused: 
 of C = 1 images go through the tiled kernel by default.  These cases aim at its own machinery: partial tile
 rows / columns, fewer tiles than CTAs, the dynamic tail of the tile schedule, windows that do not cover the
 tile (global fallback taps), homographies outside the packed division's proven domain (scalar __fdiv_rn
-path), start offsets, and - in a subprocess with DMH_TUNING=tile=2 / tile=1 - the C = 3 instantiation.
+path), start offsets, and - in a subprocess with DMH_TUNING=tile=3 - the C = 3 instantiation.
 Bars: warped pixels and masks bit-exact, loss / gradients within 1e-4 absolute (north_star).
 """
 import os
@@ -244,6 +244,6 @@ print("C3 OK")
 
 
 def test_tile_c3_instantiation_in_subprocess():
-    env = dict(os.environ, DMH_TUNING="tile=2")
+    env = dict(os.environ, DMH_TUNING="tile=3")
     r = subprocess.run([sys.executable, "-c", _C3_SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "C3 OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -221,3 +221,32 @@ def test_pairs_u8_against_data_aug(ref):
     assert torch.equal(full, torch.cat((o[0], o[1]), dim=2).permute(2, 0, 1).float())
     assert torch.equal(patch, torch.cat((o[2], o[3]), dim=2).permute(2, 0, 1).float())
     assert o[8] == [7, 11]
+
+
+def test_normalize_family(ref):
+    g = torch.Generator().manual_seed(31)
+    pix = torch.rand(2, 2, 9, 14, generator=g) * 12
+    nrm = torch.rand(2, 2, 9, 14, generator=g) * 2 - 1
+    assert torch.equal(ref.fmo.normalize(pix.clone()), port.grid_normalize(pix, 0))
+    assert torch.equal(ref.fmo.unnormalize(nrm.clone()), port.grid_normalize(nrm, 1))
+    assert torch.equal(ref.fmo.unormalise_flow_or_mapping(nrm.clone()), port.grid_normalize(nrm, 1))
+    assert torch.equal(ref.fmo.unormalise_and_convert_mapping_to_flow(nrm.clone()), port.grid_normalize(nrm, 2))
+
+
+def test_crop_patch_from_full(ref):
+    g = torch.Generator().manual_seed(32)
+    img = torch.rand(3, 2, 20, 28, generator=g)
+    start_i = torch.tensor([[[3, 2]], [[0, 0]], [[9, 6]]])
+    a = ref.utils.CropPatchFromFull((12, 10), img, start_i, rescale=False)
+    assert torch.equal(a, port.crop_patch_from_full((12, 10), img, start_i, rescale=False))
+    start_f = torch.tensor([[[3.25, 2.5]], [[-1.5, 0.75]], [[17.5, 11.25]]])     # windows that leave the image on both sides
+    b = ref.utils.CropPatchFromFull((12, 10), img, start_f, rescale=True)
+    assert torch.equal(b, port.crop_patch_from_full((12, 10), img, start_f, rescale=True))
+
+
+def test_resize_flow(ref):
+    if ref.ddpm is None:
+        pytest.skip(f"ddpm module not importable here: {getattr(ref, 'ddpm_error', '')}")
+    rs = np.random.default_rng(33)
+    fl = rs.standard_normal((36, 64, 2)).astype(np.float32) * 5
+    assert np.array_equal(ref.ddpm.resize_flow(fl.copy(), 24), port.resize_flow(fl.copy(), 24))

@@ -128,6 +128,17 @@ int main(int argc, char** argv) {
     unsigned long long t0 = ~0ull, t1 = 0;
     for (int i = 0; i < n; ++i) { if (dbg[i * 10 + 1] < t0) t0 = dbg[i * 10 + 1]; if (dbg[i * 10 + 2] > t1) t1 = dbg[i * 10 + 2]; }
     printf("debug: %d CTAs, kernel span %.1f us\n", n, (t1 - t0) * 1e-3);
+    {   // per-CTA statistics (min / mean / max): end time, producer phases, consumer-warp-0 wait
+      const char* names[6] = {"end_us", "loader done-wait kcycles", "loader free-wait (shared buffers)", "loader queue-wait", "(unused)", "consumer-warp-0 full-wait kcycles"};
+      for (int f = 0; f < 6; ++f) {
+        double mn = 1e30, mx = -1e30, sm = 0;
+        for (int i = 0; i < n; ++i) {
+          const double v = (f == 0) ? (dbg[i * 10 + 2] - t0) * 1e-3 : dbg[i * 10 + 4 + f] / 1000.0;
+          mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v;
+        }
+        printf("  %-36s min %8.1f  mean %8.1f  max %8.1f\n", names[f], mn, sm / (n > 0 ? n : 1), mx);
+      }
+    }
     for (int i = 0; i < n; ++i)
       printf("cta %3d sm %3llu start %7.1f end %7.1f us tiles %llu spins %llu  kcycles: done-wait %llu drain %llu claim %llu stage %llu full-wait %llu\n",
              i, dbg[i * 10], (dbg[i * 10 + 1] - t0) * 1e-3, (dbg[i * 10 + 2] - t0) * 1e-3, dbg[i * 10 + 3], dbg[i * 10 + 4],
