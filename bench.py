@@ -316,7 +316,7 @@ class Step:
 class PairStep(Step):
     """cfg2 (8 basis weights) and cfg4 (4-pt offsets): bidirectional warp + mask + masked L1, fwd+bwd."""
 
-    def __init__(self, ctx, workload, B, variant="dlt", api="fused"):
+    def __init__(self, ctx, workload, B, variant="dlt", api="fused", given_flow=False):
         from dmhomo_b200 import ops, synth
         from dmhomo_b200.compat import flow_and_mapping_operations as fmo, hem_utils, losses
 
@@ -337,6 +337,7 @@ class PairStep(Step):
                 par = (((torch.rand(2 * B, 4, 2, generator=gen, device=dev) * 2 - 1) * wl["rho"]).requires_grad_(True),)
             self.pairs.append(pair)
             self.sets.append((img1, img2) + par)
+        self.given_flow = given_flow      # drop-in arm without the reference's inline basis product: flows are inputs
         self.basis = hem_utils.gen_basis(h, w).to(dev) if workload == "cfg2" else None
         self.basis_ref = self.basis.reshape(1, 8, -1) if self.basis is not None else None   # the reference's (1,8,2hw) view
         self.src2 = synth.corner_points(2 * B, h, w, dev)
@@ -344,6 +345,8 @@ class PairStep(Step):
         explicit_flow = workload == "cfg2" and (variant == "direct" or api == "dropin")
         self.bytes_per_px = 24 * C + (17 if explicit_flow else 1)
         self.l1 = losses.LossL1(reduction="mean")
+        if given_flow:
+            self.flows = [tuple(ops.basis_combine(self.basis, p.detach(), h, w).requires_grad_(True) for p in s[2:]) for s in self.sets]
 
     def step(self, k, ev=None):
         ops = self.ops
@@ -353,8 +356,11 @@ class PairStep(Step):
             # the reference's own statements (HEM/model/net.py:808-818, HEM/loss/losses.py:142-146) with the patched
             # names: the basis product and the mask * image products are inline torch in the reference and stay torch
             hu, fmo = self.hem_utils, self.fmo
-            flow_f = (self.basis_ref * par[0].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
-            flow_b = (self.basis_ref * par[1].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
+            if self.given_flow:
+                flow_f, flow_b = self.flows[k]
+            else:
+                flow_f = (self.basis_ref * par[0].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
+                flow_b = (self.basis_ref * par[1].view(B, 8, 1)).sum(1).reshape(B, 2, h, w)
             ops.warp_timing_events = ev
             w2 = hu.get_warp_flow(img2, flow_f)
             self.kernel_name = ops.last_warp_kernel
@@ -387,10 +393,20 @@ class PairStep(Step):
         for s in self.sets:
             for t in s:
                 t.grad = None
+        if self.given_flow:
+            for fs in self.flows:
+                for t in fs:
+                    t.grad = None
+
+    def kernel_pixels(self):
+        return self.B * self.h * self.w if self.api == "dropin" else self.pixels
+
+    def kernel_bytes_per_px(self):
+        return 8 * self.C + 8 if self.api == "dropin" else self.bytes_per_px    # one forward warp by an explicit flow
 
     def kernel_label(self):
         if self.api == "dropin":
-            return f"{self.kernel_name}<S1,FLOW,FWD,C={self.C}> (first get_warp_flow of the call sequence)"
+            return f"{self.kernel_name}<S1,FLOW,FWD,C={self.C}> (the first get_warp_flow of the call sequence, one direction)"
         kind = "FLOW" if self.variant == "direct" and self.workload == "cfg2" else "HOMOGRAPHY"
         return f"{self.kernel_name}<S1,{kind},FUSED,C={self.C},MASKED_DIFF,dense> (both directions, one launch)"
 
@@ -703,6 +719,8 @@ def measure(ctx, st, K, W, use_graph, min_seconds, want_clocks=False, reduce_eve
     ms_block = statistics.median(blocks)
     return dict(ms_block=ms_block, ms_per_step=ms_block / K, blocks=len(blocks), kernel_ms=kern_ms, launches_per_step=int(launches_per_step),
                 clocks=clocks, loss=final_loss, graph=use_graph, run_step=run_step, graphs=graphs, g_loss=g_loss,
+                g_events=g_events,   # external events recorded inside the graphs: must outlive every replay
+
                 collectives=(reducer.collectives if reducer else 0))
 
 
@@ -711,7 +729,9 @@ def sub_result(ctx, st, m, K, scaling, desc, kernel_pixels=None, traffic_key=Non
     r = {"workload": desc, "value": px_all / (m["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": K,
          "blocks": m["blocks"], "scaling": scaling, "n_gpus": ctx.world, "launch": "CUDA graph replay" if m["graph"] else "eager",
          "gpu_launches_per_step": m["launches_per_step"], "kernel": st.kernel_label(), "kernel_ms": m["kernel_ms"],
-         "roofline": roofline(ctx, st.bytes_per_px, kernel_pixels or st.pixels, m["kernel_ms"], st.kernel_label(), traffic_key)}
+         "roofline": roofline(ctx, st.kernel_bytes_per_px() if hasattr(st, "kernel_bytes_per_px") else st.bytes_per_px,
+                              kernel_pixels or (st.kernel_pixels() if hasattr(st, "kernel_pixels") else st.pixels), m["kernel_ms"],
+                              st.kernel_label(), traffic_key)}
     if m["loss"] is not None:
         r["loss"] = m["loss"]
     if extra:
@@ -743,7 +763,17 @@ def run_side_configs(ctx, args, names):
                 what = ("cfg2, 'direct' variant: warp by the 8-basis flow itself (HEM/model/net.py:808-818), basis_combine + fused warp/mask/L1 with an explicit flow, fwd+bwd"
                         if direct else
                         "cfg2, drop-in arm: the reference's own call sequence through compat.* (get_warp_flow x2, create_border_mask x2, LossL1 x2, autograd backward); inline torch of the reference stays torch")
-                out[name] = sub_result(ctx, st, m, K, "weak", what, traffic_key=name)
+                extra = None
+                if not direct:
+                    # the same call sequence fed with the flows: what is left once the reference's inline
+                    # (basis * weight).sum(1) and its autograd backward (plain torch, not ours to replace) are taken out
+                    st2 = PairStep(ctx, "cfg2", WORKLOADS["cfg2"]["B"], variant="direct", api="dropin", given_flow=True)
+                    m2 = measure(ctx, st2, K, W, graph, 0.2)
+                    extra = {"ms_per_step_from_flows": m2["ms_per_step"],
+                             "value_from_flows": st2.pixels * ctx.world / (m2["ms_per_step"] * 1e-3) / 1e9,
+                             "gpu_launches_per_step_from_flows": m2["launches_per_step"]}
+                    del st2, m2
+                out[name] = sub_result(ctx, st, m, K, "weak", what, traffic_key=name, extra=extra)
             elif name == "cfg3":
                 st = RenderStep(ctx, WORKLOADS["cfg3"]["B"])
                 m = measure(ctx, st, K, W, graph, 0.2)
@@ -811,27 +841,40 @@ def run_side_configs(ctx, args, names):
 
 
 def time_render_ops(ctx, st):
-    """cfg3: every launch of the rendering batch on its own (CUDA events, rotating input sets)."""
+    """cfg3: every launch of the rendering batch on its own - `reps` calls over the rotating input sets captured into one
+    CUDA graph (eager calls would time the Python / ctypes launch path, not the kernels), CUDA events around the replay."""
     res = []
+    n_sets = len(st.sets)
     with torch.cuda.stream(ctx.stream), torch.no_grad():
-        n_sets = len(st.sets)
         lists = [st.ops_list(k) for k in range(n_sets)]
         for idx in range(len(lists[0])):
             for k in range(n_sets):                 # inputs of this op for every set (and a warm-up of the op itself)
                 for j in range(idx + 1):
                     lists[k][j][1]()
             ctx.stream.synchronize()
-            reps = 5 * n_sets
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ctx.stream)
-            for r in range(reps):
-                lists[r % n_sets][idx][1]()
-            e1.record(ctx.stream)
-            ctx.stream.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / reps
+            reps = 4 * n_sets
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=ctx.stream):
+                    for r in range(reps):
+                        lists[r % n_sets][idx][1]()
+                g.replay()
+                ctx.stream.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ctx.stream)
+                g.replay()
+                e1.record(ctx.stream)
+                ctx.stream.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / reps
+                del g
+            except Exception:
+                us = None
             label, _, bpp = lists[0][idx]
-            gbs = bpp * st.pixels / (us * 1e-6) / 1e9
-            res.append({"op": label, "us": us, "bytes_per_px": bpp, "achieved_gbs": gbs, "frac": gbs / ctx.peak})
+            row = {"op": label, "us": us, "bytes_per_px": bpp}
+            if us:
+                gbs = bpp * st.pixels / (us * 1e-6) / 1e9
+                row.update(achieved_gbs=gbs, frac=gbs / ctx.peak)
+            res.append(row)
     return res
 
 
@@ -960,7 +1003,8 @@ def run_ours(args):
         e2e_all = run_e2e(ctx, st, m, K)
     kernel_pixels = st.kernel_pixels() if hasattr(st, "kernel_pixels") else st.pixels
     traffic_key = args.workload if (args.variant == "dlt" and args.api == "fused") else f"{args.workload}_{args.variant if args.api == 'fused' else 'dropin'}"
-    roof = roofline(ctx, st.bytes_per_px, kernel_pixels, m["kernel_ms"], st.kernel_label(), traffic_key)
+    roof = roofline(ctx, st.kernel_bytes_per_px() if hasattr(st, "kernel_bytes_per_px") else st.bytes_per_px, kernel_pixels,
+                    m["kernel_ms"], st.kernel_label(), traffic_key)
     headline_label, launches = st.kernel_label(), m["launches_per_step"]
     final_loss, used_graph, blocks, ms_per_step, collectives, clocks = m["loss"], m["graph"], m["blocks"], m["ms_per_step"], m["collectives"], m["clocks"]
     del m

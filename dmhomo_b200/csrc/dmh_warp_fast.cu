@@ -496,7 +496,36 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
     }
     if (mode > 0) {
       FastArgs at = a;
-      const int rc = warp_tile_launch(at, n, mode, d0.C, stream);
+      const int rc = warp_tile_launch(at, n, mode, d0.C, false, stream);
+      if (rc != 1) return rc;
+    }
+  }
+  // ... and the C = 1 launches that warp by an explicit flow tensor (get_warp_flow(img, flow) and its backward, the fused
+  // loss on the reference's own basis flow): the flow tile is staged next to the source window
+  if (d0.sampler == DMH_S1 && d0.param_kind == DMH_PARAM_FLOW && d0.C == 1 && tile_mode > 0 && tuning().tile_flow > 0) {
+    int mode = -1;
+    for (int i = 0; i < n; ++i) {
+      const dmh_warp_desc& s = d[i];
+      int m = 0;
+      const bool aligned = ((reinterpret_cast<uintptr_t>(s.src) | reinterpret_cast<uintptr_t>(s.param) | reinterpret_cast<uintptr_t>(s.target) |
+                             reinterpret_cast<uintptr_t>(s.out) | reinterpret_cast<uintptr_t>(s.grad_target) |
+                             reinterpret_cast<uintptr_t>(s.grad_param) | reinterpret_cast<uintptr_t>(s.grad_out)) & 15) == 0;
+      const bool l1 = loss == DMH_LOSS_MASKED_DIFF && s.target && s.loss_acc && s.use_border_mask;
+      if (!aligned || s.soft_mask || s.grad_soft_mask) {
+        m = 0;
+      } else if (pass == PASS_FUSED) {
+        m = (l1 && s.grad_src && s.grad_target && s.grad_param && !s.grad_out) ? 6 : 0;
+      } else if (pass == PASS_FWD) {
+        m = (s.out && loss == DMH_LOSS_NONE) ? 1 : 0;
+      } else {
+        m = (s.grad_out && loss == DMH_LOSS_NONE && !s.grad_loss && (s.grad_src || s.grad_param)) ? 12 : 0;
+      }
+      mode = (i == 0 || m == mode) ? m : 0;
+      if (mode == 0) break;
+    }
+    if (mode > 0) {
+      FastArgs at = a;
+      const int rc = warp_tile_launch(at, n, mode, d0.C, true, stream);
       if (rc != 1) return rc;
     }
   }

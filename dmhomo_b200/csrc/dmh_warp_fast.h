@@ -45,9 +45,10 @@ struct FastArgs {
 // launched, 1 when the request is outside the lean path (caller falls back to the general kernel).
 int warp_fast_try(const dmh_warp_desc* descs, int n, int pass, cudaStream_t stream);
 
-// Persistent, TMA staged, packed-fp32 form of the dense S1 homography launches.  mode = bits 1 (warped output +
-// validity mask) | 2 (masked L1 against the target) | 4 (gradients in the same pass).  Returns 1 when the shape is
-// outside what it takes.
-int warp_tile_launch(FastArgs& a, int n, int mode, int C, cudaStream_t stream);
+// Persistent, TMA staged, packed-fp32 form of the dense S1 launches.  mode = bits 1 (warped output + validity mask) |
+// 2 (masked L1 against the target) | 4 (gradients in the same pass) | 8 (upstream gradient instead of a loss: the
+// backward of a plain warp); flow_param: explicit flow tensor instead of one homography per sample.  Returns 1 when
+// the shape is outside what it takes.
+int warp_tile_launch(FastArgs& a, int n, int mode, int C, bool flow_param, cudaStream_t stream);
 
 }  // namespace dmh

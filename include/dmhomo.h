@@ -140,8 +140,9 @@ DMH_API const char* dmh_last_kernel_name(void);
  *   "tile"          0 scalar kernels only | 1 TMA tile kernel for the dense C = 1 launches | 2 also the gradient-free
  *                   C = 3 launches (default) | 3 also the C = 3 training launch
  *   "tile_interior" bit 0 interior-tile body, bit 1 mixed-tile body of the tile kernel (default 3)
+ *   "tile_flow"     1 (default): the C = 1 launches that warp by an explicit flow go to the tile kernel, 0: scalar kernels
  *   "tile_dyn"      percent of a tile launch's tile list handed out dynamically, the rest is split statically
- *                   (default -1: 15 for the C = 1 training launch, 100 otherwise)
+ *                   (default -1: 0 for the C = 1 training launch, 100 otherwise)
  *   "tile_chunk"    longest run of tiles per dynamic claim, 1 .. 8; runs shrink to single tiles at the end
  *                   (default -1: 1 / 4 / 8 for the C = 1 training, C = 3 training and gradient-free launches)
  * The library reads no environment variables.  Unknown key: DMH_EINVAL. */

@@ -15,6 +15,7 @@ import pytest
 import torch
 
 from dmhomo_b200 import ops, synth
+from dmhomo_b200.compat import hem_utils
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -130,6 +131,7 @@ _AB_SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, %r)
 from dmhomo_b200 import ops, synth
+from dmhomo_b200.compat import hem_utils
 from oracle import port
 g = lambda s: torch.Generator().manual_seed(s)
 B, h, w = 6, 320, 576
@@ -216,6 +218,7 @@ _C3_SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, %r)
 from dmhomo_b200 import ops, synth
+from dmhomo_b200.compat import hem_utils
 from oracle import port
 g = lambda s: torch.Generator().manual_seed(s)
 B, C, h, w = 2, 3, 128, 192
@@ -247,3 +250,87 @@ def test_tile_c3_instantiation_in_subprocess():
     env = dict(os.environ, DMH_TUNING="tile=3")
     r = subprocess.run([sys.executable, "-c", _C3_SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "C3 OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------- explicit flow on the tile kernel
+def _flows(B, h, w, seed):
+    """A smooth basis-like flow (what HEM predicts), a noisy one (taps all over the window), and one that throws part of
+    the tile far outside the staged window (global fallback path)."""
+    gen = g(seed)
+    basis = hem_utils.gen_basis(h, w)
+    smooth = ops.basis_combine(basis.to(DEV), synth.basis_weights(B, gen, 4.0).to(DEV), h, w).cpu()
+    noisy = smooth + torch.randn(B, 2, h, w, generator=gen) * 3.0
+    wild = smooth.clone()
+    wild[:, :, ::7, ::5] += 90.0
+    wild[:, 0, 40:60, 100:130] -= 300.0
+    return {"smooth": smooth, "noisy": noisy, "wild": wild}
+
+
+@pytest.mark.parametrize("kind", ["smooth", "noisy", "wild"])
+def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
+    from dmhomo_b200 import _lib
+
+    B, C, h, w = 3, 1, 128, 192
+    img = synth.noise_images(B, C, h, w, g(151))
+    flow = _flows(B, h, w, 152)[kind]
+    gout = torch.randn(B, C, h, w, generator=g(153))
+    ic, fc = img.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    ref = port.get_warp_flow(ic, fc)
+    (ref * gout).sum().backward()
+
+    res = {}
+    for tile_flow in (1, 0):
+        _lib.set_tuning(tile_flow=tile_flow)
+        try:
+            ig, fg = img.to(DEV).requires_grad_(True), flow.to(DEV).requires_grad_(True)
+            out = hem_utils.get_warp_flow(ig, fg)
+            kern_f = ops.last_warp_kernel
+            (out * gout.to(DEV)).sum().backward()
+            kern_b = ops.last_warp_kernel
+        finally:
+            _lib.set_tuning(tile_flow=1)
+        assert ("tile" in kern_f) == bool(tile_flow) and ("tile" in kern_b) == bool(tile_flow), (kern_f, kern_b)
+        assert torch.equal(out.detach().cpu(), ref.detach()), "warped pixels differ from the oracle"
+        assert (ig.grad.cpu() - ic.grad).abs().max().item() < 1e-4
+        assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4 * max(1.0, fc.grad.abs().max().item())
+        res[tile_flow] = (out.detach(), ig.grad, fg.grad)
+    assert torch.equal(res[1][2], res[0][2]), "dL/dflow differs between the tile and the scalar kernel"
+    assert (res[1][1] - res[0][1]).abs().max().item() < 1e-4      # scattered sums: order differs
+
+    # only one of the two gradients wanted
+    ig = img.to(DEV).requires_grad_(True)
+    (hem_utils.get_warp_flow(ig, flow.to(DEV)) * gout.to(DEV)).sum().backward()
+    assert (ig.grad - res[1][1]).abs().max().item() < 1e-4
+    fg = flow.to(DEV).requires_grad_(True)
+    (hem_utils.get_warp_flow(img.to(DEV), fg) * gout.to(DEV)).sum().backward()
+    assert torch.equal(fg.grad, res[1][2])
+
+
+def test_tile_flow_fused_loss_direct_variant():
+    """The reference's own training warp (HEM/model/net.py:808-818): warp by the basis flow, masked L1, gradients to both
+    images and both flows in one launch."""
+    from dmhomo_b200 import _lib
+
+    B, C, h, w = 4, 1, 160, 256
+    gen = g(154)
+    img1, img2 = synth.smooth_images(B, C, h, w, gen), synth.smooth_images(B, C, h, w, gen)
+    fl = _flows(B, h, w, 155)
+    ff, fb = fl["smooth"], fl["noisy"]
+    leaves_c = [t.clone().requires_grad_(True) for t in (img1, img2, ff, fb)]
+    a, b, ffc, fbc = leaves_c
+    mf, mb = port.border_mask(ffc).unsqueeze(1), port.border_mask(fbc).unsqueeze(1)
+    ref = port.masked_l1(mf, a, port.get_warp_flow(b, ffc)) + port.masked_l1(mb, b, port.get_warp_flow(a, fbc))
+    ref.backward()
+    for tile_flow in (1, 0):
+        _lib.set_tuning(tile_flow=tile_flow)
+        try:
+            lg = [t.to(DEV).requires_grad_(True) for t in (img1, img2, ff, fb)]
+            loss = ops.warp_loss([ops.WarpTerm(lg[1], lg[0], lg[2]), ops.WarpTerm(lg[0], lg[1], lg[3])], kind=ops.PARAM_FLOW,
+                                 border_mask=True)
+            assert ("tile" in ops.last_warp_kernel) == bool(tile_flow)
+            loss.backward()
+        finally:
+            _lib.set_tuning(tile_flow=1)
+        assert abs(loss.item() - ref.item()) < 1e-5
+        for tg, tc in zip(lg, leaves_c):
+            assert (tg.grad.cpu() - tc.grad).abs().max().item() < 1e-4
