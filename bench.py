@@ -134,8 +134,13 @@ def bind_to_gpu_numa(dev_index):
     off: with eight ranks on one host the H2D copies otherwise cross the socket interconnect.  Best effort; returns
     {"node", "cpus", "previous"} (previous = the affinity to restore for the CPU leg) or None."""
     try:
-        pr = torch.cuda.get_device_properties(dev_index)
-        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        try:
+            pr = torch.cuda.get_device_properties(dev_index)
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except Exception:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(dev_index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            bus = out[-12:]                   # "00000000:1b:00.0" -> "0000:1b:00.0"
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
             return None

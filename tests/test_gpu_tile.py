@@ -277,6 +277,12 @@ def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
     ic, fc = img.clone().requires_grad_(True), flow.clone().requires_grad_(True)
     ref = port.get_warp_flow(ic, fc)
     (ref * gout).sum().backward()
+    # Far out-of-bounds coordinates clamp both taps to the border pixel with weights +d and -d (d = distance, up to 300
+    # here): the border pixels of dL/dimg are sums of thousands of cancelling terms, so the reference's own fp32 result
+    # is noise there.  Yardstick: the same pipeline in fp64; the kernels must be as close to it as the fp32 oracle is.
+    i64, f64 = img.double().requires_grad_(True), flow.double().requires_grad_(True)
+    (port.get_warp_flow(i64, f64) * gout.double()).sum().backward()
+    img_tol = max(1e-4, 4.0 * (ic.grad.double() - i64.grad).abs().max().item())
 
     res = {}
     for tile_flow in (1, 0):
@@ -291,16 +297,17 @@ def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
             _lib.set_tuning(tile_flow=1)
         assert ("tile" in kern_f) == bool(tile_flow) and ("tile" in kern_b) == bool(tile_flow), (kern_f, kern_b)
         assert torch.equal(out.detach().cpu(), ref.detach()), "warped pixels differ from the oracle"
-        assert (ig.grad.cpu() - ic.grad).abs().max().item() < 1e-4
+        assert (ig.grad.cpu()[..., 1:-1, 1:-1] - ic.grad[..., 1:-1, 1:-1]).abs().max().item() < 1e-4
+        assert (ig.grad.cpu().double() - i64.grad).abs().max().item() < img_tol
         assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4 * max(1.0, fc.grad.abs().max().item())
         res[tile_flow] = (out.detach(), ig.grad, fg.grad)
     assert torch.equal(res[1][2], res[0][2]), "dL/dflow differs between the tile and the scalar kernel"
-    assert (res[1][1] - res[0][1]).abs().max().item() < 1e-4      # scattered sums: order differs
+    assert (res[1][1] - res[0][1]).abs().max().item() < 2 * img_tol      # scattered sums: order differs
 
     # only one of the two gradients wanted
     ig = img.to(DEV).requires_grad_(True)
     (hem_utils.get_warp_flow(ig, flow.to(DEV)) * gout.to(DEV)).sum().backward()
-    assert (ig.grad - res[1][1]).abs().max().item() < 1e-4
+    assert (ig.grad - res[1][1]).abs().max().item() < 2 * img_tol
     fg = flow.to(DEV).requires_grad_(True)
     (hem_utils.get_warp_flow(img.to(DEV), fg) * gout.to(DEV)).sum().backward()
     assert torch.equal(fg.grad, res[1][2])
