@@ -95,6 +95,7 @@ SIGNATURES = {
     "dmh_l1_backward": [_fp, _fp, _i64, _fp, _f, _fp, _fp, _fp],
     "dmh_flow_to_rgb": [_fp, _fp, _i, _i, _i, _f, _i, _i, _fp],
     "dmh_warp_perspective": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
+    "dmh_warp_perspective_u8": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_eval_point_error": [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_to_homography_ls": [_fp, _fp, _fp, _i, _i, _i, _fp],
     "dmh_pairs_u8_to_gray": [_fp, _fp, _fp, _fp, _fp, C.POINTER(_d), C.POINTER(_d), _i, _i, _i, _i, _i, _i, _fp],

@@ -7,7 +7,7 @@ import torch
 from .. import ops
 
 __all__ = ["mesh_grid", "norm_grid", "flow_warp", "homo_to_flow", "adapt_homography_to_preprocessing_v3",
-           "flow_to_image", "visulize_flow", "postProcess", "postProcess_cv2", "homo_gen", "photo_loss", "resize_flow"]
+           "flow_to_image", "visulize_flow", "postProcess", "postProcess_cv2", "homo_gen", "photo_loss", "resize_flow", "warp_pairs_u8", "split_sample_batches"]
 
 
 def mesh_grid(B, H, W):
@@ -104,3 +104,25 @@ def resize_flow(flow, size):
     f = torch.as_tensor(np.ascontiguousarray(flow, dtype=np.float32), device="cuda").permute(2, 0, 1).unsqueeze(0)
     out = ops.flow_upsample(f.contiguous(), (int(size), int(size)), if_rate=True, align_corners=False)
     return out[0].permute(1, 2, 0).contiguous().cpu().numpy()
+
+
+def warp_pairs_u8(imgs, homos):
+    """The check DGM/generate_nyps_to_single_case.py:10-21 runs on the generated {"imgs": (N,6,H,W) uint8, "homos": (N,3,3)}
+    sample batches (DGM/dgm_sample.py:62-76): cv2.warpPerspective(img1, homo12, (W,H)) on the uint8 image, batched on the
+    GPU, bit-identical to OpenCV's fixed-point path.  numpy in, numpy (N,3,H,W) uint8 out."""
+    x = torch.as_tensor(np.ascontiguousarray(imgs[:, :3]), device="cuda")
+    H = torch.as_tensor(np.asarray(homos, dtype=np.float64).reshape(-1, 3, 3), device="cuda")
+    N, _, h, w = x.shape
+    return ops.warp_perspective(x, H, (w, h)).cpu().numpy()
+
+
+def split_sample_batches(buf):
+    """generate_nyps_to_single_case.py:29-47: the list of {"imgs", "homos"} batches a sampling run saved ->
+    one {"img12": (6,H,W) uint8, "homo12": (3,3)} dict per sample, the on-disk pair format the HEM loader reads
+    (HEM/dataset/data_loader.py:121-146).  Host-side bookkeeping, no arithmetic."""
+    out = []
+    for item in buf:
+        imgs, homos = item["imgs"], item["homos"]
+        for i in range(len(imgs)):
+            out.append({"img12": imgs[i], "homo12": homos[i]})
+    return out

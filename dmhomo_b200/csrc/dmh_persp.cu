@@ -26,23 +26,37 @@ __device__ __forceinline__ bool invert3(const double* s, double* t) {
 
 // One thread per destination pixel; all channels.  Coordinates follow OpenCV's
 // warpPerspective: per 64-wide block X0 = M0*bx + M1*y + M2, then (X0 + M0*x1) * (32 / W),
-// rounded half-to-even to 1/32 pixel; bilinear taps weighted by the float table entries
-// (1-fy)(1-fx) ..; constant-zero border per tap.  ddpm.py:1520-1529, data_loader.py:151.
-__global__ void __launch_bounds__(256) warp_persp_kernel(const float* __restrict__ src, const double* __restrict__ H,
-                                                         float* __restrict__ dst, int B, int C, int Hs, int Ws, int h,
+// rounded half-to-even to 1/32 pixel; constant-zero border per tap.  ddpm.py:1520-1529, data_loader.py:151,
+// generate_nyps_to_single_case.py:15.
+//   float32 images: bilinear taps weighted by the float table entries (1-fy)(1-fx) ..
+//   uint8 images:   OpenCV's fixed-point remap - the same table scaled to 2^15 (exact integers at 1/32 steps),
+//                   (sum w_i p_i + 2^14) >> 15; bit-identical to cv2 on uint8 (tests/test_oracle_golden.py).
+// The inverse of H is taken once per CTA (one fp64 division instead of one per thread).
+template <typename T>
+__global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ src, const double* __restrict__ H,
+                                                         T* __restrict__ dst, int B, int C, int Hs, int Ws, int h,
                                                          int w, int cl, int bw0) {
+  constexpr bool kU8 = sizeof(T) == 1;
   const int b = blockIdx.z;
   const int x = blockIdx.x * 64 + (threadIdx.x & 63);
   const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  __shared__ double Ms[9];
+  if (threadIdx.x == 0) {
+    double Hm[9], Mi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hm[k] = __ldg(H + (size_t)b * 9 + k);
+    if (!invert3(Hm, Mi)) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Mi[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ms[k] = Mi[k];
+  }
+  __syncthreads();
   if (x >= w || y >= h) return;
   double M[9];
-  double Hm[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) Hm[k] = __ldg(H + (size_t)b * 9 + k);
-  if (!invert3(Hm, M)) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) M[k] = 0.0;
-  }
+  for (int k = 0; k < 9; ++k) M[k] = Ms[k];
   const int bx = (x / bw0) * bw0, x1 = x - bx;
   const double dbx = (double)bx, dy = (double)y, dx1 = (double)x1;
   const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dbx), __dmul_rn(M[1], dy)), M[2]);
@@ -55,33 +69,42 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const float* __restrict
   const double fY = fmax(lo, fmin(hi, __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), Wd)));
   const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
   const int sx = X >> 5, sy = Y >> 5;
-  const float ax = div_rn((float)(X & 31), 32.0f), ay = div_rn((float)(Y & 31), 32.0f);
+  const int iax = X & 31, iay = Y & 31;
+  const float ax = div_rn((float)iax, 32.0f), ay = div_rn((float)iay, 32.0f);
   const float bx0 = sub_rn(1.0f, ax), by0 = sub_rn(1.0f, ay);
   const float w00 = mul_rn(by0, bx0), w01 = mul_rn(by0, ax), w10 = mul_rn(ay, bx0), w11 = mul_rn(ay, ax);
+  // (1-fy)(1-fx) * 2^15 with fx, fy multiples of 1/32: (32-iay)(32-iax) * 32, exact
+  const int i00 = (32 - iay) * (32 - iax) * 32, i01 = (32 - iay) * iax * 32, i10 = iay * (32 - iax) * 32, i11 = iay * iax * 32;
   const bool x0in = (sx >= 0 && sx < Ws), x1in = (sx + 1 >= 0 && sx + 1 < Ws);
   const bool y0in = (sy >= 0 && sy < Hs), y1in = (sy + 1 >= 0 && sy + 1 < Hs);
   const int cx0 = min(max(sx, 0), Ws - 1), cx1 = min(max(sx + 1, 0), Ws - 1);
   const int cy0 = min(max(sy, 0), Hs - 1), cy1 = min(max(sy + 1, 0), Hs - 1);
   for (int c = 0; c < C; ++c) {
-    float v00, v01, v10, v11;
+    T v00, v01, v10, v11;
     if (cl) {
-      const float* sp = src + (size_t)b * Hs * Ws * C + c;
+      const T* sp = src + (size_t)b * Hs * Ws * C + c;
       v00 = __ldg(sp + ((size_t)cy0 * Ws + cx0) * C);
       v01 = __ldg(sp + ((size_t)cy0 * Ws + cx1) * C);
       v10 = __ldg(sp + ((size_t)cy1 * Ws + cx0) * C);
       v11 = __ldg(sp + ((size_t)cy1 * Ws + cx1) * C);
     } else {
-      const float* sp = src + ((size_t)b * C + c) * Hs * Ws;
+      const T* sp = src + ((size_t)b * C + c) * Hs * Ws;
       v00 = __ldg(sp + (size_t)cy0 * Ws + cx0);
       v01 = __ldg(sp + (size_t)cy0 * Ws + cx1);
       v10 = __ldg(sp + (size_t)cy1 * Ws + cx0);
       v11 = __ldg(sp + (size_t)cy1 * Ws + cx1);
     }
-    v00 = (x0in && y0in) ? v00 : 0.f;
-    v01 = (x1in && y0in) ? v01 : 0.f;
-    v10 = (x0in && y1in) ? v10 : 0.f;
-    v11 = (x1in && y1in) ? v11 : 0.f;
-    const float o = add_rn(add_rn(add_rn(mul_rn(v00, w00), mul_rn(v01, w01)), mul_rn(v10, w10)), mul_rn(v11, w11));
+    v00 = (x0in && y0in) ? v00 : (T)0;
+    v01 = (x1in && y0in) ? v01 : (T)0;
+    v10 = (x0in && y1in) ? v10 : (T)0;
+    v11 = (x1in && y1in) ? v11 : (T)0;
+    T o;
+    if (kU8) {
+      const int acc = (int)v00 * i00 + (int)v01 * i01 + (int)v10 * i10 + (int)v11 * i11;
+      o = (T)((acc + (1 << 14)) >> 15);
+    } else {
+      o = (T)add_rn(add_rn(add_rn(mul_rn((float)v00, w00), mul_rn((float)v01, w01)), mul_rn((float)v10, w10)), mul_rn((float)v11, w11));
+    }
     if (cl)
       dst[(((size_t)b * h + y) * w + x) * C + c] = o;
     else
@@ -222,8 +245,10 @@ __device__ __forceinline__ void solve8_warp_ls(double (&m)[9], int lane, double 
 
 using namespace dmh;
 
-extern "C" int dmh_warp_perspective(const float* src, const double* H, float* dst, int B, int C, int Hs, int Ws, int h,
-                                    int w, int channels_last, void* stream) {
+namespace {
+template <typename T>
+int warp_perspective_launch(const T* src, const double* H, T* dst, int B, int C, int Hs, int Ws, int h, int w, int channels_last,
+                            void* stream) {
   DMH_REQUIRE(src && H && dst, "warp_perspective: null pointer");
   DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hs > 0 && Ws > 0 && h > 0 && w > 0, "warp_perspective: bad size");
   // OpenCV's block geometry (BLOCK_SZ = 32): bh0 = min(16, h); bw0 = min(1024 / bh0, w)
@@ -231,8 +256,19 @@ extern "C" int dmh_warp_perspective(const float* src, const double* H, float* ds
   int bw0 = 1024 / bh0;
   bw0 = bw0 < w ? bw0 : w;
   dim3 grid((unsigned)((w + 63) / 64), (unsigned)((h + 3) / 4), (unsigned)B);
-  warp_persp_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, H, dst, B, C, Hs, Ws, h, w, channels_last, bw0);
+  warp_persp_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(src, H, dst, B, C, Hs, Ws, h, w, channels_last, bw0);
   return launched("warp_persp_kernel");
+}
+}  // namespace
+
+extern "C" int dmh_warp_perspective(const float* src, const double* H, float* dst, int B, int C, int Hs, int Ws, int h,
+                                    int w, int channels_last, void* stream) {
+  return warp_perspective_launch<float>(src, H, dst, B, C, Hs, Ws, h, w, channels_last, stream);
+}
+
+extern "C" int dmh_warp_perspective_u8(const uint8_t* src, const double* H, uint8_t* dst, int B, int C, int Hs, int Ws, int h,
+                                       int w, int channels_last, void* stream) {
+  return warp_perspective_launch<uint8_t>(src, H, dst, B, C, Hs, Ws, h, w, channels_last, stream);
 }
 
 extern "C" int dmh_flow_to_homography_ls(const float* flow, double* H, double* workspace, int B, int h, int w,

@@ -38,6 +38,7 @@ struct FastArgs {
   // tiled persistent kernel (dmh_warp_tile.cu): length of the tile list, "start offsets are benign" flag
   int n_tiles, start_sane;
   int n_static, dyn_chunk, counter_slot;   // schedule: statically split prefix of the tile list, tiles per dynamic claim, counter slot
+  int pair_major;               // tile list ordered (sample, term, tile) instead of (term, sample, tile)
   int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body (dmh_set_tuning "tile_interior")
 };
 

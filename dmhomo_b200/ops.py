@@ -855,9 +855,11 @@ def flow_to_rgb(flow, max_flow=256.0, in_channels_last=False, out_channels_last=
 
 def warp_perspective(img, H, dsize, channels_last=False):
     """cv2.warpPerspective(img, H, dsize=(w,h)) with default flags, batched (ddpm.py:1520-1529).
-    img (B,C,Hs,Ws) [or (B,Hs,Ws,C)] fp32; H (B,3,3) (any float dtype; used as float64)."""
+    img (B,C,Hs,Ws) [or (B,Hs,Ws,C)] fp32 - or uint8, which takes OpenCV's fixed-point path and returns uint8
+    (generate_nyps_to_single_case.py:15); H (B,3,3) (any float dtype; used as float64)."""
     dev = _cuda(img, H)
-    im = _f32(img)
+    u8 = img.dtype == torch.uint8
+    im = img.contiguous() if u8 else _f32(img)
     Hc = H.to(torch.float64).contiguous()
     if channels_last:
         B, Hs, Ws, Cc = im.shape
@@ -866,10 +868,10 @@ def warp_perspective(img, H, dsize, channels_last=False):
     w, h = int(dsize[0]), int(dsize[1])
     if Hc.numel() != B * 9:
         raise ValueError("warp_perspective: H must be (B,3,3)")
-    out = torch.empty((B, h, w, Cc) if channels_last else (B, Cc, h, w), device=dev, dtype=torch.float32)
+    out = torch.empty((B, h, w, Cc) if channels_last else (B, Cc, h, w), device=dev, dtype=im.dtype)
+    fn = L.lib().dmh_warp_perspective_u8 if u8 else L.lib().dmh_warp_perspective
     with torch.cuda.device(dev):
-        L.check(L.lib().dmh_warp_perspective(_p(im), _p(Hc), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last),
-                                             _stream(dev)), "warp_perspective")
+        L.check(fn(_p(im), _p(Hc), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last), _stream(dev)), "warp_perspective")
     return out
 
 

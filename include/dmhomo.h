@@ -141,6 +141,7 @@ DMH_API const char* dmh_last_kernel_name(void);
  *                   C = 3 launches (default) | 3 also the C = 3 training launch
  *   "tile_interior" bit 0 interior-tile body, bit 1 mixed-tile body of the tile kernel (default 3)
  *   "tile_flow"     1 (default): the C = 1 launches that warp by an explicit flow go to the tile kernel, 0: scalar kernels
+ *   "tile_pair_major" 1 (default): two-term tile launches walk (sample, term, tile), 0: (term, sample, tile)
  *   "tile_dyn"      percent of a tile launch's tile list handed out dynamically, the rest is split statically
  *                   (default -1: 0 for the C = 1 training launch, 100 otherwise)
  *   "tile_chunk"    longest run of tiles per dynamic claim, 1 .. 8; runs shrink to single tiles at the end
@@ -264,6 +265,10 @@ DMH_API int dmh_flow_to_rgb(const float* flow, float* rgb, int B, int h, int w, 
  * src: channels_last ? (B,Hs,Ws,C) : (B,C,Hs,Ws); dst likewise with (h,w); H (B,3,3) double. */
 DMH_API int dmh_warp_perspective(const float* src, const double* H, float* dst, int B, int C, int Hs, int Ws,
                          int h, int w, int channels_last, void* stream);
+/* The same call on uint8 images (generate_nyps_to_single_case.py:15 warps the uint8 halves of the {"imgs","homos"}
+ * sample batches): OpenCV's fixed-point remap, weights (1-fy)(1-fx) * 2^15, (sum + 2^14) >> 15; bit-identical to cv2. */
+DMH_API int dmh_warp_perspective_u8(const uint8_t* src, const double* H, uint8_t* dst, int B, int C, int Hs, int Ws,
+                            int h, int w, int channels_last, void* stream);
 
 /* --- evaluation metric (A18) --------------------------------------------------------------- */
 /* compute_eval_results(): per sample mean over P points of min(err(p1->p2, flow_f), err(p2->p1, flow_b)),

@@ -212,3 +212,30 @@ def test_warp_eval_and_warp_into(C, h, w):
     valid = torch.full((B, h, w), 9, dtype=torch.uint8, device=DEV)
     ops.warp_into(img2, H[:B], out, valid, kind=ops.PARAM_HOMOGRAPHY)
     assert torch.equal(out, w2) and torch.equal(valid.bool(), m2)
+
+
+def test_warp_perspective_u8_matches_cv2_bit_for_bit():
+    """uint8 S4: the {"imgs","homos"} sample batches and their cv2.warpPerspective check."""
+    import cv2
+
+    from dmhomo_b200 import synth
+    from dmhomo_b200.compat import dgm
+
+    rs = np.random.default_rng(66)
+    N, h, w = 5, 256, 256
+    imgs = rs.integers(0, 256, size=(N, 6, h, w), dtype=np.uint8)
+    H360 = synth.homographies_360x640(N, synth.generator(), 32.0)
+    homos = np.stack([dgm.adapt_homography_to_preprocessing_v3(360, 640, H360[i], h, w) for i in range(N)])
+    ours = dgm.warp_pairs_u8(imgs, homos)
+    assert ours.dtype == np.uint8 and ours.shape == (N, 3, h, w)
+    for i in range(N):
+        ref = cv2.warpPerspective(np.ascontiguousarray(imgs[i, :3].transpose(1, 2, 0)), homos[i], (w, h)).transpose(2, 0, 1)
+        assert np.array_equal(ours[i], ref), f"sample {i}: {np.abs(ours[i].astype(int) - ref.astype(int)).max()} LSB off"
+    # channels-last, non-square, partial blocks
+    img = torch.from_numpy(rs.integers(0, 256, size=(2, 100, 132, 3), dtype=np.uint8))
+    Hm = np.stack([np.diag([132 / 640, 100 / 360, 1.0]) @ H360[i] @ np.diag([640 / 132, 360 / 100, 1.0]) for i in range(2)])
+    out = ops.warp_perspective(img.to(DEV), torch.from_numpy(Hm).to(DEV), (132, 100), channels_last=True).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(out[i], cv2.warpPerspective(img[i].numpy(), Hm[i], (132, 100)))
+    samples = dgm.split_sample_batches([{"imgs": imgs[:2], "homos": homos[:2]}, {"imgs": imgs[2:], "homos": homos[2:]}])
+    assert len(samples) == N and samples[3]["img12"].shape == (6, h, w) and np.array_equal(samples[3]["homo12"], homos[3])

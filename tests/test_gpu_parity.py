@@ -26,6 +26,14 @@ def rel_fro(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
+def close_to_fp64(name, cuda, ref32, ref64, atol=ATOL):
+    """Sums of many signed terms (dL/dH, dL/dweights): the CUDA result has to be as close to an fp64 evaluation of the
+    same pipeline as the reference's own fp32 arithmetic is, or within north_star's 1e-4 - whichever is larger."""
+    e_cuda = (cuda.detach().double().cpu() - ref64).abs().max().item()
+    e_ref = (ref32.detach().double() - ref64).abs().max().item()
+    assert e_cuda <= max(atol, 1.05 * e_ref), f"{name}: |cuda - fp64| = {e_cuda:.3e} vs |oracle fp32 - fp64| = {e_ref:.3e}"
+
+
 # ---------------------------------------------------------------------------------- DLT
 @pytest.mark.parametrize("B,h,w,rho", [(16, 360, 640, 32.0), (64, 320, 576, 32.0), (7, 1080, 1920, 64.0)])
 def test_dlt4_matches_oracle(B, h, w, rho):
@@ -350,10 +358,14 @@ def test_fused_bidirectional_loss_stage_isolated(fused, C):
     loss.backward()
     assert (i1g.grad.cpu() - i1c.grad).abs().max().item() < ATOL
     assert (i2g.grad.cpu() - i2c.grad).abs().max().item() < ATOL
-    # gradients to H are sums over all pixels of signed terms: compare relative to their size
-    for a, b in ((Hfg.grad.cpu(), Hfc.grad), (Hbg.grad.cpu(), Hbc.grad)):
-        assert ((a - b).abs() / (b.abs() + 1e-2)).max().item() < 2e-2
-        assert rel_fro(a, b) < 1e-3
+    # gradients to H are sums over all pixels of signed terms: yardstick = the same pipeline in fp64
+    i1d, i2d = img1.double().requires_grad_(True), img2.double().requires_grad_(True)
+    Hfd, Hbd = Hf.double().requires_grad_(True), Hb.double().requires_grad_(True)
+    ffd, fbd = port.homography_to_flow(Hfd, h, w)[0], port.homography_to_flow(Hbd, h, w)[0]
+    mfd, mbd = port.border_mask(ffd).unsqueeze(1).double(), port.border_mask(fbd).unsqueeze(1).double()
+    (port.masked_l1(mfd, i1d, port.get_warp_flow(i2d, ffd)) + port.masked_l1(mbd, i2d, port.get_warp_flow(i1d, fbd))).backward()
+    close_to_fp64("dL/dHf", Hfg.grad, Hfc.grad, Hfd.grad)
+    close_to_fp64("dL/dHb", Hbg.grad, Hbc.grad, Hbd.grad)
 
 
 def test_fused_loss_upstream_scaling_and_weight():
@@ -540,8 +552,11 @@ def test_cfg2_pipeline(variant):
     loss.backward()
     for tg, tc in zip(leaves_g[:2], leaves_c[:2]):
         assert (tg.grad.cpu() - tc.grad).abs().max().item() < ATOL
-    for tg, tc in zip(leaves_g[2:], leaves_c[2:]):
-        assert (tg.grad.cpu() - tc.grad).abs().max().item() < ATOL + 2e-2 * tc.grad.abs().max().item()
+    leaves_d = [t.double().requires_grad_(True) for t in (img1, img2, wf, wb)]
+    port.pipeline_basis(leaves_d[0], leaves_d[1], basis.double().reshape(1, 8, -1), leaves_d[2], leaves_d[3], variant=variant,
+                        backward=True)
+    for name, tg, tc, td in zip(("dL/dw_f", "dL/dw_b"), leaves_g[2:], leaves_c[2:], leaves_d[2:]):
+        close_to_fp64(name, tg.grad, tc.grad, td.grad)
 
 
 def test_basis_homography_fused_matches_unfused():
@@ -568,9 +583,14 @@ def test_basis_homography_fused_matches_unfused():
     sd = src.to(DEV)
     Hf2 = ops.dlt4(sd, sd + ops.basis_corner_offsets(bd, wf.to(DEV), h, w))
     assert torch.equal(Hf.detach(), Hf2)
-    for tg, tc in ((wfg, wfc), (wbg, wbc)):
-        scale = max(1.0, tc.grad.abs().max().item())
-        assert (tg.grad.cpu() - tc.grad).abs().max().item() < 1e-3 * scale
+    wfd, wbd = wf.double().requires_grad_(True), wb.double().requires_grad_(True)
+    b64, s64 = basis.double().reshape(1, 8, -1), src.double()
+    ((port.dlt4(s64, s64 + port.basis_corner_offsets(b64, wfd, h, w)) * gH[0].double()).sum() +
+     (port.dlt4(s64, s64 + port.basis_corner_offsets(b64, wbd, h, w)) * gH[1].double()).sum()).backward()
+    for name, tg, tc, td in (("dL/dw_f", wfg, wfc, wfd), ("dL/dw_b", wbg, wbc, wbd)):
+        # relative yardstick: these gradients are O(1e2..1e4) (random dL/dH through an 8x8 solve of condition ~1e6)
+        scale = max(1.0, td.grad.abs().max().item())
+        close_to_fp64(name, tg.grad / scale, tc.grad / scale, td.grad / scale)
 
 
 # ---------------------------------------------------------------------------------- DGM rendering

@@ -179,3 +179,20 @@ def test_pipeline_basis_golden():
     assert (leaves[0].grad - d["g_img1"]).abs().max().item() < 1e-6
     assert (leaves[1].grad - d["g_img2"]).abs().max().item() < 1e-6
     assert rel_fro(leaves[2].grad, d["g_wf"]) < 1e-3 and rel_fro(leaves[3].grad, d["g_wb"]) < 1e-3
+
+
+def test_warp_perspective_u8_emulation_matches_cv2():
+    """The uint8 path of cv2.warpPerspective (the reference warps the uint8 halves of its generated samples,
+    DGM/generate_nyps_to_single_case.py:15): the oracle's restatement of OpenCV's fixed-point remap is bit-identical to
+    cv2 itself - OpenCV is unpinned by the reference, cv2 (4.13 here) is the oracle of record."""
+    import cv2
+    import numpy as np
+
+    from dmhomo_b200 import synth
+
+    rs = np.random.default_rng(7)
+    Hs = synth.homographies_360x640(3, synth.generator(), 32.0)
+    for i, (h, w) in enumerate(((256, 256), (90, 160), (100, 132))):
+        img = rs.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        Hm = np.diag([w / 640, h / 360, 1.0]) @ Hs[i] @ np.diag([640 / w, 360 / h, 1.0])
+        assert np.array_equal(cv2.warpPerspective(img, Hm, (w, h)), port.warp_perspective_emul_u8(img, Hm, (w, h)))
