@@ -471,8 +471,8 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
   if (tiles > 2147483647LL) return 1;
   // ---- the persistent TMA tile kernel takes the dense S1 homography launches (dmh_warp_tile.cu) ----
   const int tile_mode = tuning().tile;
-  // tuning "tile": 0 never | 1 C = 1 | 2 also the gradient-free C = 3 launches (default) | 3 also the C = 3 training launch
-  // (measured: the scalar kernel below is still the faster one there, profiles/r2_kernels.txt)
+  // tuning "tile": 0 never | 1 C = 1 | 2 also the gradient-free C = 3 launches | 3 also the C = 3 training launch (default:
+  // with the pair-major tile order it beats the scalar kernel below, 0.95 vs 1.13 ms on 128 pairs 3x512x512)
   if (d0.sampler == DMH_S1 && d0.param_kind == DMH_PARAM_HOMOGRAPHY && pass != PASS_BWD && tile_mode > 0 &&
       (d0.C == 1 || tile_mode > (pass == PASS_FUSED ? 2 : 1))) {
     int mode = -1;

@@ -446,20 +446,25 @@ def _plan_grad_slots(flat, terms, needs, kind, base):
     parameter are plain stores: every (term, slot) gets its own buffer and autograd sums them (the reference passes
     one mask to both terms when params.normalize_mask is set, HEM/loss/losses.py:129).  Sharing is by tensor
     identity, never by storage address: two distinct leaves that alias one storage each get their own gradient.
-    `flat` holds the tensors (or their ids) in apply() order."""
+    `flat` holds the tensors (or their ids) in apply() order.  Returns (slots, zero_end, total): only [0, zero_end)
+    needs zeroing, the plain-store buffers behind it are fully overwritten by the kernels."""
     accumulated = (0, 1) + ((2,) if kind in (PARAM_HOMOGRAPHY, PARAM_BASIS8) else ())
     slots, owners, total = {}, {}, base
-    for i, tl in enumerate(terms):
-        for s in (0, 1, 2, 3):
-            if tl[s] is None or not needs[i * _SLOTS + s]:
-                continue
-            obj = flat[i * _SLOTS + s]
-            key = (obj if isinstance(obj, int) else id(obj)) if s in accumulated else ("own", i, s)
-            if key not in owners:
-                owners[key] = (total, tl[s].numel())
-                total += tl[s].numel()
-            slots[(i, s)] = owners[key]
-    return slots, total
+    zero_end = base
+    for want_accumulated in (True, False):      # accumulated buffers first: only [0, zero_end) has to be zeroed
+        for i, tl in enumerate(terms):
+            for s in (0, 1, 2, 3):
+                if tl[s] is None or not needs[i * _SLOTS + s] or (s in accumulated) != want_accumulated:
+                    continue
+                obj = flat[i * _SLOTS + s]
+                key = (obj if isinstance(obj, int) else id(obj)) if want_accumulated else ("own", i, s)
+                if key not in owners:
+                    owners[key] = (total, tl[s].numel())
+                    total += tl[s].numel()
+                slots[(i, s)] = owners[key]
+        if want_accumulated:
+            zero_end = total
+    return slots, zero_end, total
 
 
 class _WarpLoss(torch.autograd.Function):
@@ -487,8 +492,9 @@ class _WarpLoss(torch.autograd.Function):
         fused = bool(cfg["fused"]) and any_grad
         # one flat zeroed workspace: [loss accumulators (double) | gradients of every distinct input]
         acc_floats = 2 * n * B
-        slots, total = _plan_grad_slots(flat, terms, needs, cfg["kind"], acc_floats) if fused else ({}, acc_floats)
-        ws = torch.zeros(total, device=dev, dtype=torch.float32)
+        slots, zero_end, total = _plan_grad_slots(flat, terms, needs, cfg["kind"], acc_floats) if fused else ({}, acc_floats, acc_floats)
+        ws = torch.empty(total, device=dev, dtype=torch.float32)
+        ws[:zero_end].zero_()
         acc = ws[:acc_floats].view(torch.float64)
 
         def gbuf(i, s):
@@ -544,8 +550,9 @@ class _WarpLoss(torch.autograd.Function):
             bas_c, per = saved[0], saved[1]
             flat = saved[2:2 + n * _SLOTS]
             terms = [flat[i * _SLOTS:(i + 1) * _SLOTS] for i in range(n)]
-            slots, total = _plan_grad_slots(ctx.input_ids, terms, needs, cfg["kind"], 0)
-            ws = torch.zeros(max(total, 1), device=dev, dtype=torch.float32)
+            slots, zero_end, total = _plan_grad_slots(ctx.input_ids, terms, needs, cfg["kind"], 0)
+            ws = torch.empty(max(total, 1), device=dev, dtype=torch.float32)
+            ws[:zero_end].zero_()
             cfgacc = 0
 
             def gbuf(i, s):

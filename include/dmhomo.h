@@ -138,14 +138,14 @@ DMH_API uint64_t dmh_launch_count(void);
 DMH_API const char* dmh_last_kernel_name(void);
 /* Development knobs, process-wide, read at launch time (defaults = the measured best; none changes a result):
  *   "tile"          0 scalar kernels only | 1 TMA tile kernel for the dense C = 1 launches | 2 also the gradient-free
- *                   C = 3 launches (default) | 3 also the C = 3 training launch
+ *                   C = 3 launches | 3 also the C = 3 training launch (default)
  *   "tile_interior" bit 0 interior-tile body, bit 1 mixed-tile body of the tile kernel (default 3)
  *   "tile_flow"     1 (default): the C = 1 launches that warp by an explicit flow go to the tile kernel, 0: scalar kernels
- *   "tile_pair_major" 1 (default): two-term tile launches walk (sample, term, tile), 0: (term, sample, tile)
+ *   "tile_pair_major" 1: two-term tile launches walk (sample, term, tile), 0: (term, sample, tile); default -1: 1 at C = 3
  *   "tile_dyn"      percent of a tile launch's tile list handed out dynamically, the rest is split statically
  *                   (default -1: 0 for the C = 1 training launch, 100 otherwise)
  *   "tile_chunk"    longest run of tiles per dynamic claim, 1 .. 8; runs shrink to single tiles at the end
- *                   (default -1: 1 / 4 / 8 for the C = 1 training, C = 3 training and gradient-free launches)
+ *                   (default -1: 1 for the C = 1 training launch, 8 otherwise)
  * The library reads no environment variables.  Unknown key: DMH_EINVAL. */
 DMH_API int dmh_set_tuning(const char* key, int value);
 DMH_API int dmh_get_tuning(const char* key, int* value);

@@ -107,7 +107,7 @@ def _forward_parity(img, H, tile):
         out, mask = ops.warp(img.to(DEV), H.to(DEV), kind=ops.PARAM_HOMOGRAPHY, return_mask=True)
         kernel = ops.last_warp_kernel
     finally:
-        _lib.set_tuning(tile=2)
+        _lib.set_tuning(tile=3)
     flow, _ = port.homography_to_flow(H, h, w)
     ref, idx_ref = port.get_warp_flow(img, flow, return_indices=True)
     assert torch.equal(mask.cpu(), port.correspondence_mask(flow)), "validity mask differs"
@@ -122,7 +122,7 @@ def test_cfg2_full_batch_random_homographies_against_oracle():
     gen = _gen(2301)
     img1, img2 = synth.noise_images(B, C, h, w, gen), synth.noise_images(B, C, h, w, gen)
     Hf, Hb = _random_h(B, h, w, c["rho"], 2302), _random_h(B, h, w, c["rho"], 2303)
-    kernel, flow, idx_ref = _forward_parity(img2, Hf, tile=2)
+    kernel, flow, idx_ref = _forward_parity(img2, Hf, tile=3)
     assert "tile" in kernel
     _, _, idx = ops.warp(img2[:8].to(DEV), Hf[:8].to(DEV), kind=ops.PARAM_HOMOGRAPHY, return_mask=True, return_indices=True)
     assert torch.equal(idx.cpu(), idx_ref[:, :8]), "integer sample indices differ"
@@ -144,9 +144,9 @@ def test_cfg2_full_batch_random_homographies_against_oracle():
 @pytest.mark.parametrize("tile", [1, 2, 3])
 def test_cfg4_subset_random_homographies_against_oracle(tile):
     """A cfg4 subset (3x512x512 pairs, rho = 32) on the scalar kernels (tile = 1), on the tile kernel for the
-    gradient-free launches (2, the default) and on the tile kernel throughout (3)."""
+    gradient-free launches only (2) and on the tile kernel throughout (3, the default)."""
     c = synth.CONFIGS["cfg4"]
-    B, C, h, w = (64 if tile == 2 else 16), c["C"], c["h"], c["w"]   # 64 pairs on the default dispatch
+    B, C, h, w = (64 if tile == 3 else 16), c["C"], c["h"], c["w"]   # 64 pairs on the default dispatch
     gen = _gen(2304)
     img1, img2 = synth.noise_images(B, C, h, w, gen), synth.noise_images(B, C, h, w, gen)
     Hf, Hb = _random_h(B, h, w, c["rho"], 2305), _random_h(B, h, w, c["rho"], 2306)
@@ -162,7 +162,7 @@ def test_cfg4_subset_random_homographies_against_oracle(tile):
         assert ("tile" in ops.last_warp_kernel) == (tile >= 3)
         loss.backward()
     finally:
-        _lib.set_tuning(tile=2)
+        _lib.set_tuning(tile=3)
     assert abs(loss.item() - l32.item()) < 1e-5
     assert (i1.grad.cpu() - g1_32).abs().max().item() < ATOL
     assert (i2.grad.cpu() - g2_32).abs().max().item() < ATOL
@@ -235,3 +235,34 @@ def test_tile_schedule_share_does_not_change_results(dyn):
     assert abs(base[2].item() - other[2].item()) < 1e-6
     assert (base[3] - other[3]).abs().max().item() < 1e-7 and (base[4] - other[4]).abs().max().item() < 1e-7
     assert ((base[5] - other[5]).norm() / base[5].norm()).item() < 1e-4
+
+
+def test_pair_major_order_does_not_change_results():
+    """Two-term launches walk the tile list (sample, term, tile) at C = 3 - both directions of a pair back to back, so the
+    second use of every image / gradient line hits the L2 - or (term, sample, tile): same tiles, same results."""
+    B, C, h, w = 6, 3, 128, 192
+    gen = _gen(2313)
+    img1, img2 = synth.noise_images(B, C, h, w, gen).to(DEV), synth.noise_images(B, C, h, w, gen).to(DEV)
+    Hf, Hb = _random_h(B, h, w, 12.0, 2314).to(DEV), _random_h(B, h, w, 12.0, 2315).to(DEV)
+
+    def run():
+        loss_e, outs, masks = ops.warp_eval([ops.WarpTerm(img2, img1, Hf), ops.WarpTerm(img1, img2, Hb)], kind=ops.PARAM_HOMOGRAPHY)
+        i1, i2 = img1.clone().requires_grad_(True), img2.clone().requires_grad_(True)
+        hf, hb = Hf.clone().requires_grad_(True), Hb.clone().requires_grad_(True)
+        loss = ops.warp_loss([ops.WarpTerm(i2, i1, hf), ops.WarpTerm(i1, i2, hb)], kind=ops.PARAM_HOMOGRAPHY)
+        assert "tile" in ops.last_warp_kernel
+        loss.backward()
+        return loss_e, outs, masks, loss.detach(), i1.grad, i2.grad, hf.grad, hb.grad
+
+    res = {}
+    for pm in (1, 0):
+        _lib.set_tuning(tile_pair_major=pm)
+        try:
+            res[pm] = run()
+        finally:
+            _lib.set_tuning(tile_pair_major=-1)
+    a, b = res[1], res[0]
+    assert torch.equal(a[1][0], b[1][0]) and torch.equal(a[1][1], b[1][1]) and torch.equal(a[2][0], b[2][0])
+    assert abs(a[0].item() - b[0].item()) < 1e-6 and abs(a[3].item() - b[3].item()) < 1e-6
+    assert (a[4] - b[4]).abs().max().item() < 1e-6 and (a[5] - b[5]).abs().max().item() < 1e-6
+    assert ((a[6] - b[6]).norm() / b[6].norm()).item() < 1e-4 and ((a[7] - b[7]).norm() / b[7].norm()).item() < 1e-4
