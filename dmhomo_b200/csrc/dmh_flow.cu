@@ -284,19 +284,23 @@ __global__ void __launch_bounds__(kThreads) zero_border_mask_kernel(const float*
 }
 
 // ---- A13: LossL1 (HEM/loss/losses.py:10-17) ---------------------------------------------------------
+// 128-bit loads (n4 = number of float4 groups when both pointers are 16-byte aligned, else 0) + scalar tail
 __global__ void __launch_bounds__(kThreads) l1_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                          long long n, double* __restrict__ acc) {
+                                                          long long n, long long n4, double* __restrict__ acc) {
   float s = 0.f;
   double sd = 0.0;
   int cnt = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    s += fabsf(__ldg(a + i) - __ldg(b + i));
-    if (++cnt == 64) {  // bound the fp32 partial
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long i = t0; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    s += (fabsf(x.x - y.x) + fabsf(x.y - y.y)) + (fabsf(x.z - y.z) + fabsf(x.w - y.w));
+    if (++cnt == 16) {  // bound the fp32 partial (64 terms)
       sd += (double)s;
       s = 0.f;
       cnt = 0;
     }
   }
+  for (long long i = 4 * n4 + t0; i < n; i += stride) s += fabsf(__ldg(a + i) - __ldg(b + i));
   sd += (double)s;
   sd = warp_sum(sd);
   __shared__ double red[kThreads / 32];
@@ -311,10 +315,17 @@ __global__ void __launch_bounds__(kThreads) l1_sum_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(kThreads) l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                          long long n, const float* __restrict__ g, float scale,
+                                                          long long n, long long n4, const float* __restrict__ g, float scale,
                                                           float* __restrict__ ga, float* __restrict__ gb) {
   const float gs = (g ? __ldg(g) : 1.f) * scale;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long i = t0; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    const float4 v = make_float4(gs * sign_of(x.x - y.x), gs * sign_of(x.y - y.y), gs * sign_of(x.z - y.z), gs * sign_of(x.w - y.w));
+    if (ga) reinterpret_cast<float4*>(ga)[i] = v;
+    if (gb) reinterpret_cast<float4*>(gb)[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
+  }
+  for (long long i = 4 * n4 + t0; i < n; i += stride) {
     const float v = gs * sign_of(__ldg(a + i) - __ldg(b + i));
     if (ga) ga[i] = v;
     if (gb) gb[i] = -v;
@@ -533,7 +544,8 @@ extern "C" int dmh_zero_border_mask(const float* image, uint8_t* mask, int B, in
 extern "C" int dmh_l1_sum(const float* a, const float* b, int64_t n, double* acc, void* stream) {
   DMH_REQUIRE(a && b && acc, "l1_sum: null pointer");
   DMH_REQUIRE(n > 0, "l1_sum: n must be positive");
-  l1_sum_kernel<<<blocks_for(n, kThreads * 4), kThreads, 0, as_stream(stream)>>>(a, b, n, acc);
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  l1_sum_kernel<<<blocks_for(n, kThreads * 16), kThreads, 0, as_stream(stream)>>>(a, b, n, vec ? n / 4 : 0, acc);
   return launched("l1_sum_kernel");
 }
 
@@ -541,7 +553,8 @@ extern "C" int dmh_l1_backward(const float* a, const float* b, int64_t n, const 
                                float* gb, void* stream) {
   DMH_REQUIRE(a && b && (ga || gb), "l1_backward: null pointer");
   DMH_REQUIRE(n > 0, "l1_backward: n must be positive");
-  l1_bwd_kernel<<<blocks_for(n), kThreads, 0, as_stream(stream)>>>(a, b, n, g, scale, ga, gb);
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ga) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0;
+  l1_bwd_kernel<<<blocks_for(n, kThreads * 4), kThreads, 0, as_stream(stream)>>>(a, b, n, vec ? n / 4 : 0, g, scale, ga, gb);
   return launched("l1_bwd_kernel");
 }
 

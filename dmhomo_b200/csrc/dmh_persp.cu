@@ -79,25 +79,21 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ s
   const bool y0in = (sy >= 0 && sy < Hs), y1in = (sy + 1 >= 0 && sy + 1 < Hs);
   const int cx0 = min(max(sx, 0), Ws - 1), cx1 = min(max(sx + 1, 0), Ws - 1);
   const int cy0 = min(max(sy, 0), Hs - 1), cy1 = min(max(sy + 1, 0), Hs - 1);
+  // tap offsets inside one plane (32-bit; the host checks Hs * Ws * C < 2^31) and their border flags, once for all channels
+  const int o00 = cy0 * Ws + cx0, o01 = cy0 * Ws + cx1, o10 = cy1 * Ws + cx0, o11 = cy1 * Ws + cx1;
+  const bool in00 = x0in && y0in, in01 = x1in && y0in, in10 = x0in && y1in, in11 = x1in && y1in;
+  const int plane_s = Hs * Ws, plane_d = h * w;
+  const T* sp = src + (size_t)b * C * plane_s;
+  T* dp = dst + (size_t)b * C * plane_d + (cl ? (y * w + x) * C : y * w + x);
+  const int tap_mul = cl ? C : 1, chan_s = cl ? 1 : plane_s, chan_d = cl ? 1 : plane_d;
+#pragma unroll 3
   for (int c = 0; c < C; ++c) {
-    T v00, v01, v10, v11;
-    if (cl) {
-      const T* sp = src + (size_t)b * Hs * Ws * C + c;
-      v00 = __ldg(sp + ((size_t)cy0 * Ws + cx0) * C);
-      v01 = __ldg(sp + ((size_t)cy0 * Ws + cx1) * C);
-      v10 = __ldg(sp + ((size_t)cy1 * Ws + cx0) * C);
-      v11 = __ldg(sp + ((size_t)cy1 * Ws + cx1) * C);
-    } else {
-      const T* sp = src + ((size_t)b * C + c) * Hs * Ws;
-      v00 = __ldg(sp + (size_t)cy0 * Ws + cx0);
-      v01 = __ldg(sp + (size_t)cy0 * Ws + cx1);
-      v10 = __ldg(sp + (size_t)cy1 * Ws + cx0);
-      v11 = __ldg(sp + (size_t)cy1 * Ws + cx1);
-    }
-    v00 = (x0in && y0in) ? v00 : (T)0;
-    v01 = (x1in && y0in) ? v01 : (T)0;
-    v10 = (x0in && y1in) ? v10 : (T)0;
-    v11 = (x1in && y1in) ? v11 : (T)0;
+    const T* spc = sp + c * chan_s;
+    T v00 = __ldg(spc + o00 * tap_mul), v01 = __ldg(spc + o01 * tap_mul), v10 = __ldg(spc + o10 * tap_mul), v11 = __ldg(spc + o11 * tap_mul);
+    v00 = in00 ? v00 : (T)0;
+    v01 = in01 ? v01 : (T)0;
+    v10 = in10 ? v10 : (T)0;
+    v11 = in11 ? v11 : (T)0;
     T o;
     if (kU8) {
       const int acc = (int)v00 * i00 + (int)v01 * i01 + (int)v10 * i10 + (int)v11 * i11;
@@ -105,10 +101,7 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ s
     } else {
       o = (T)add_rn(add_rn(add_rn(mul_rn((float)v00, w00), mul_rn((float)v01, w01)), mul_rn((float)v10, w10)), mul_rn((float)v11, w11));
     }
-    if (cl)
-      dst[(((size_t)b * h + y) * w + x) * C + c] = o;
-    else
-      dst[(((size_t)b * C + c) * h + y) * w + x] = o;
+    dp[c * chan_d] = o;
   }
 }
 
@@ -251,6 +244,7 @@ int warp_perspective_launch(const T* src, const double* H, T* dst, int B, int C,
                             void* stream) {
   DMH_REQUIRE(src && H && dst, "warp_perspective: null pointer");
   DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hs > 0 && Ws > 0 && h > 0 && w > 0, "warp_perspective: bad size");
+  DMH_REQUIRE((long long)Hs * Ws * C < 2147483647LL && (long long)h * w * C < 2147483647LL, "warp_perspective: image too large");
   // OpenCV's block geometry (BLOCK_SZ = 32): bh0 = min(16, h); bw0 = min(1024 / bh0, w)
   const int bh0 = h < 16 ? h : 16;
   int bw0 = 1024 / bh0;
