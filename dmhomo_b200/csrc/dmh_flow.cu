@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(kThreads) h2flow_f64_kernel(const double* __re
   }
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // ---- A12: basis combine (HEM/model/net.py:808-815) ------------------------------------------------
 // One thread = one pixel; the 16 basis values stay in registers while the thread loops over the
 // batch, so the shared basis tensor is read once per launch instead of once per sample.
@@ -205,6 +207,40 @@ __global__ void __launch_bounds__(kThreads) basis_combine_kernel(const float* __
   }
 }
 
+// Four pixels per thread (plane % 4 == 0): 128-bit loads and stores, same per-pixel operation order.
+__global__ void __launch_bounds__(kThreads, 2) basis_combine4_kernel(const float* __restrict__ basis,
+                                                                     const float* __restrict__ weight,
+                                                                     float* __restrict__ flow, int B, long long plane4,
+                                                                     int b_per_block) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= plane4) return;
+  const float4* bs = reinterpret_cast<const float4*>(basis);
+  float4* out = reinterpret_cast<float4*>(flow);
+  float4 bv[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) bv[k] = __ldg(bs + (size_t)k * plane4 + q);
+  const int b0 = blockIdx.y * b_per_block, b1 = min(B, b0 + b_per_block);
+  for (int b = b0; b < b1; ++b) {
+    const float* wp = weight + (size_t)b * 8;
+    const float w0 = __ldg(wp);
+    float4 fx = make_float4(mul_rn(bv[0].x, w0), mul_rn(bv[0].y, w0), mul_rn(bv[0].z, w0), mul_rn(bv[0].w, w0));
+    float4 fy = make_float4(mul_rn(bv[1].x, w0), mul_rn(bv[1].y, w0), mul_rn(bv[1].z, w0), mul_rn(bv[1].w, w0));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float wk = __ldg(wp + k);
+      const float4 cx = bv[2 * k], cy = bv[2 * k + 1];
+      fx.x = add_rn(fx.x, mul_rn(cx.x, wk)); fx.y = add_rn(fx.y, mul_rn(cx.y, wk));
+      fx.z = add_rn(fx.z, mul_rn(cx.z, wk)); fx.w = add_rn(fx.w, mul_rn(cx.w, wk));
+      fy.x = add_rn(fy.x, mul_rn(cy.x, wk)); fy.y = add_rn(fy.y, mul_rn(cy.y, wk));
+      fy.z = add_rn(fy.z, mul_rn(cy.z, wk)); fy.w = add_rn(fy.w, mul_rn(cy.w, wk));
+    }
+    out[((size_t)b * 2) * plane4 + q] = fx;
+    out[((size_t)b * 2 + 1) * plane4 + q] = fy;
+  }
+}
+
+// dL/dw[b,k] = sum_px ( gflow[b,0,px] * basis[k,0,px] + gflow[b,1,px] * basis[k,1,px] ): a skinny (B x 2hw) x (2hw x 8) product.
+// General form (any plane size): one sample per CTA row, the basis re-read per sample from the L2.
 __global__ void __launch_bounds__(kThreads) basis_combine_bwd_kernel(const float* __restrict__ basis,
                                                                      const float* __restrict__ gflow,
                                                                      float* __restrict__ gw, int B, int h, int w) {
@@ -232,6 +268,63 @@ __global__ void __launch_bounds__(kThreads) basis_combine_bwd_kernel(const float
 #pragma unroll
     for (int q = 0; q < kThreads / 32; ++q) v += red[q][threadIdx.x];
     red_add(gw + (size_t)b * 8 + threadIdx.x, v);
+  }
+}
+
+// plane % 4 == 0: a thread keeps the 16 basis values of its four pixels in registers (64) and walks kBwdSamples
+// samples, two 128-bit loads of the upstream gradient each; the eight partial sums of a sample are reduced across the
+// warp at once by a transposing butterfly (4 + 2 + 1 + 2 shuffles, lane l ends up with the total of one k) instead of
+// eight separate warp sums. The basis is read B / kBwdSamples times from the L2 (per-sample kernel above: B times, 755
+// MB of L2 reads and 82 us at cfg2's size; holding 8 samples x 8 sums per thread instead: 168 registers, 186 us).
+constexpr int kBwdSamples = 8;
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
+__global__ void __launch_bounds__(kThreads, 2) basis_combine_bwd4_kernel(const float* __restrict__ basis,
+                                                                         const float* __restrict__ gflow,
+                                                                         float* __restrict__ gw, int B, long long plane4) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = q < plane4;
+  const float4* bs = reinterpret_cast<const float4*>(basis);
+  const float4* gs = reinterpret_cast<const float4*>(gflow);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bv[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) bv[k] = valid ? __ldg(bs + (size_t)k * plane4 + q) : zero;
+  const int b0 = blockIdx.y * kBwdSamples;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const bool o1 = lane & 1, o2 = lane & 2, o4 = lane & 4;
+  float tot[kBwdSamples];
+#pragma unroll
+  for (int s = 0; s < kBwdSamples; ++s) {
+    const bool have = valid && b0 + s < B;
+    const float4 gx = have ? __ldg(gs + ((size_t)(b0 + s) * 2) * plane4 + q) : zero;
+    const float4 gy = have ? __ldg(gs + ((size_t)(b0 + s) * 2 + 1) * plane4 + q) : zero;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = dot4(gy, bv[2 * k + 1], dot4(gx, bv[2 * k], 0.f));
+    float r4[4], r2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r4[i] = (o1 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, o1 ? v[i] : v[i + 4], 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r2[i] = (o2 ? r4[i + 2] : r4[i]) + __shfl_xor_sync(0xffffffffu, o2 ? r4[i] : r4[i + 2], 2);
+    float r = (o4 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, o4 ? r2[0] : r2[1], 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    tot[s] = r;   // the warp's sum for k = 4*bit0 + 2*bit1 + bit2 of the lane
+  }
+  __shared__ float red[kThreads / 32][kBwdSamples * 8];
+  if (lane < 8) {
+    const int k = ((lane & 1) << 2) | (lane & 2) | ((lane >> 2) & 1);
+#pragma unroll
+    for (int s = 0; s < kBwdSamples; ++s) red[wrp][s * 8 + k] = tot[s];
+  }
+  __syncthreads();
+  if (threadIdx.x < kBwdSamples * 8 && b0 + (int)(threadIdx.x >> 3) < B) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < kThreads / 32; ++w8) v += red[w8][threadIdx.x];
+    red_add(gw + (size_t)(b0 + (threadIdx.x >> 3)) * 8 + (threadIdx.x & 7), v);
   }
 }
 
@@ -498,14 +591,20 @@ extern "C" int dmh_basis_combine(const float* basis, const float* weight, float*
   DMH_REQUIRE(basis && weight && flow, "basis_combine: null pointer");
   DMH_REQUIRE(B > 0 && h > 0 && w > 0, "basis_combine: bad size");
   const long long plane = (long long)h * w;
-  const unsigned bx = (unsigned)((plane + kThreads - 1) / kThreads);
+  const bool vec = plane % 4 == 0 && aligned16(basis) && aligned16(flow);
+  const long long items = vec ? plane / 4 : plane;
+  const unsigned bx = (unsigned)((items + kThreads - 1) / kThreads);
   // enough CTAs for a few waves, but as many samples per CTA as possible (basis reuse)
-  int by = (int)((4LL * kNumSMs * 8 + bx - 1) / bx);
+  int by = (int)(((vec ? 4LL : 32LL) * kNumSMs + bx - 1) / bx);
   by = by < 1 ? 1 : (by > B ? B : by);
   const int b_per_block = (B + by - 1) / by;
   by = (B + b_per_block - 1) / b_per_block;
-  basis_combine_kernel<<<dim3(bx, (unsigned)by), kThreads, 0, as_stream(stream)>>>(basis, weight, flow, B, h, w,
-                                                                                   b_per_block);
+  if (vec)
+    basis_combine4_kernel<<<dim3(bx, (unsigned)by), kThreads, 0, as_stream(stream)>>>(basis, weight, flow, B, items,
+                                                                                      b_per_block);
+  else
+    basis_combine_kernel<<<dim3(bx, (unsigned)by), kThreads, 0, as_stream(stream)>>>(basis, weight, flow, B, h, w,
+                                                                                     b_per_block);
   return launched("basis_combine_kernel");
 }
 
@@ -514,9 +613,16 @@ extern "C" int dmh_basis_combine_backward(const float* basis, const float* grad_
   DMH_REQUIRE(basis && grad_flow && grad_weight, "basis_combine_backward: null pointer");
   DMH_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0, "basis_combine_backward: bad size");
   const long long plane = (long long)h * w;
-  long long chunks = (plane + kThreads * 8 - 1) / (kThreads * 8);
-  basis_combine_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)B), kThreads, 0, as_stream(stream)>>>(
-      basis, grad_flow, grad_weight, B, h, w);
+  if (plane % 4 == 0 && aligned16(basis) && aligned16(grad_flow)) {
+    const long long plane4 = plane / 4;
+    const unsigned gx = (unsigned)((plane4 + kThreads - 1) / kThreads);
+    const unsigned gy = (unsigned)((B + kBwdSamples - 1) / kBwdSamples);
+    basis_combine_bwd4_kernel<<<dim3(gx, gy), kThreads, 0, as_stream(stream)>>>(basis, grad_flow, grad_weight, B, plane4);
+  } else {
+    long long chunks = (plane + kThreads * 8 - 1) / (kThreads * 8);
+    basis_combine_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)B), kThreads, 0, as_stream(stream)>>>(
+        basis, grad_flow, grad_weight, B, h, w);
+  }
   return launched("basis_combine_bwd_kernel");
 }
 

@@ -769,3 +769,26 @@ def test_elementwise_kernels_scalar_and_vector_paths(h, w):
     flow = torch.randn(B, 2, h, w, generator=g(92)) * (w / 2)
     assert torch.equal(ops.border_mask(flow.to(DEV)).cpu(), port.correspondence_mask(flow))
     assert torch.equal(ops.border_mask(flow.to(DEV), as_float=True).cpu(), port.border_mask(flow).reshape(B, h, w))
+
+
+@pytest.mark.parametrize("B,h,w", [(11, 64, 96), (64, 320, 576), (3, 50, 70), (5, 45, 71)])
+def test_basis_combine_backward_groups(B, h, w):
+    """flow = sum_k w_k basis_k (HEM/model/net.py:808-815) and dL/dweights: four pixels per thread when the plane allows
+    (45 x 71 does not: scalar kernels), sample groups of 8 per CTA with a ragged last group - the forward bit-exact, the
+    backward against an fp64 evaluation."""
+    gen = g(260)
+    basis = hem_utils.gen_basis(h, w)
+    wt = synth.basis_weights(B, gen, 3.0)
+    gflow = torch.randn(B, 2, h, w, generator=gen)
+    w64 = wt.double().requires_grad_(True)
+    (port.basis_combine(basis.double().reshape(1, 8, -1), w64, h, w) * gflow.double()).sum().backward()
+    w32 = wt.clone().requires_grad_(True)
+    (port.basis_combine(basis.reshape(1, 8, -1), w32, h, w) * gflow).sum().backward()
+    wg = wt.to(DEV).requires_grad_(True)
+    flow = ops.basis_combine(basis.to(DEV), wg, h, w)
+    assert torch.equal(flow.detach().cpu(), port.basis_combine_sequential(basis.reshape(1, 8, -1), wt, h, w))
+    if (2 * h * w) % 32 == 0:   # torch's CPU sum associates the tail elements of a row differently (oracle/port.py)
+        assert torch.equal(flow.detach().cpu(), port.basis_combine(basis.reshape(1, 8, -1), wt, h, w))
+    (flow * gflow.to(DEV)).sum().backward()
+    scale = max(1.0, w64.grad.abs().max().item())
+    close_to_fp64("dL/dw", wg.grad.reshape(B, 8) / scale, w32.grad.reshape(B, 8) / scale, w64.grad.reshape(B, 8) / scale)
