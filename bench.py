@@ -509,6 +509,9 @@ class RenderStep(Step):
                     ev[1].record()
         return None
 
+    def kernel_bytes_per_px(self):
+        return 8 * self.C          # the S4 launch alone: source read + output written (the batch's total is bytes_per_px)
+
     def kernel_label(self):
         return "warp_perspective_kernel (cv2-exact S4, fp64 fixed-point coordinates)"
 
