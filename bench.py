@@ -284,11 +284,17 @@ class Ctx:
         return [float(x) for x in t.tolist()]
 
 
-def traffic_for(key):
-    """dram__bytes per launch of the dominant kernel from the committed ncu pass (profiles/traffic.json), or None."""
+def traffic_for(key, pixels=None):
+    """dram__bytes per launch of the dominant kernel from the committed ncu pass (profiles/traffic.json), or None; scaled
+    by the pixel count where this rank's launch covers fewer pixels than the captured one (N > 1 of a strong-scaled config)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(key)
+        d = json.load(open(path))
+        tr = d.get(key)
+        cap = d.get("_pixels", {}).get(key)
+        if tr and cap and pixels and pixels != cap:
+            tr = int(tr * (pixels / cap))
+        return tr
     except Exception:
         return None
 
@@ -298,7 +304,7 @@ def roofline(ctx, bytes_per_px, pixels, kernel_ms, kernel, traffic_key=None):
         return None
     alg = bytes_per_px * pixels
     ach = alg / (kernel_ms * 1e-3) / 1e9
-    tr = traffic_for(traffic_key) if traffic_key else None
+    tr = traffic_for(traffic_key, pixels) if traffic_key else None
     r = {"bound": "hbm", "achieved": ach, "peak": ctx.peak, "unit": "GB/s", "frac": ach / ctx.peak, "traffic": tr, "kernel": kernel,
          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg, "peak_source": ctx.peak_src}
     if tr:

@@ -9,9 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = {}
 meta = {"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one launch, ncu --set full --clock-control none)"}
 UNITS = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-for arg in sys.argv[1:]:
-    if arg.startswith("--commit"):
-        continue
+args = sys.argv[1:]
+if "--commit" in args:
+    del args[args.index("--commit"):args.index("--commit") + 2]
+for arg in args:
     key, _, rep = arg.partition("=")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -31,5 +32,9 @@ for arg in sys.argv[1:]:
     print(f"{key}: {tot / 1e6:.1f} MB per launch, {vals[dur_i]} {units[dur_i]} under ncu")
 if "--commit" in sys.argv:
     meta["commit"] = sys.argv[sys.argv.index("--commit") + 1]
+# output pixels of the captured launch (one GPU): bench.py scales the bytes when a rank's launch covers fewer (N > 1, strong scaling)
+PIXELS = {"cfg1": 2 * 16 * 360 * 640, "cfg2": 2 * 64 * 320 * 576, "cfg2_direct": 2 * 64 * 320 * 576, "cfg3": 25 * 256 * 256,
+          "cfg4": 2 * 4096 * 512 * 512, "cfg5": 512 * 1080 * 1920}
+out["_pixels"] = {k: PIXELS[k] for k in out if k in PIXELS}
 out["_meta"] = meta
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
