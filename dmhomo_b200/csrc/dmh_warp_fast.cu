@@ -85,8 +85,12 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
   const int h = a.h, w = a.w, Hs = a.Hs, Ws = a.Ws;
   int t = blockIdx.x;
   const int per = a.tiles_x * a.tiles_y;
-  const int b = t / per;
-  t -= b * per;
+  // a launch over C = groups x CT channels walks (sample, channel group) pairs: the planes of a group are contiguous
+  // ((b * C + g * CT) = bv * CT), everything per sample (flow, masks, H, accumulators) is indexed by b
+  const int bv = t / per;
+  t -= bv * per;
+  const int b = (a.groups > 1) ? bv / a.groups : bv;
+  const bool first_group = (a.groups <= 1) || (bv == b * a.groups);
   const int tyi = t / a.tiles_x, txi = t - tyi * a.tiles_x;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int x = txi * TW + (wrp % WX) * 32 + lane;
@@ -96,21 +100,21 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
   const unsigned plane_o = (unsigned)(h * w), plane_s = (unsigned)(Hs * Ws);
 
   // sample-b bases; every access below is base[32-bit offset]
-  const float* __restrict__ src = pin(tm.src + (size_t)b * CT * plane_s);
-  const float* __restrict__ tgt = kLoss ? pin(tm.target + (size_t)b * CT * plane_o) : nullptr;
-  const float* __restrict__ gout = (!kDense && PASS == PASS_BWD && tm.grad_out) ? tm.grad_out + (size_t)b * CT * plane_o : nullptr;
+  const float* __restrict__ src = pin(tm.src + (size_t)bv * CT * plane_s);
+  const float* __restrict__ tgt = kLoss ? pin(tm.target + (size_t)bv * CT * plane_o) : nullptr;
+  const float* __restrict__ gout = (!kDense && PASS == PASS_BWD && tm.grad_out) ? tm.grad_out + (size_t)bv * CT * plane_o : nullptr;
   const float* __restrict__ soft = (!kDense && tm.soft_mask) ? tm.soft_mask + (size_t)b * plane_o : nullptr;
   const float* __restrict__ flow = (PARAM == DMH_PARAM_FLOW) ? tm.param + (size_t)b * 2 * plane_o : nullptr;
   const bool has_out = kOut && (kDense ? (PASS == PASS_FWD) : (tm.out != nullptr));
-  const bool has_valid = kOut && (kDense ? (PASS == PASS_FWD) : (tm.valid != nullptr));
+  const bool has_valid = kOut && (kDense ? (PASS == PASS_FWD) : (tm.valid != nullptr)) && first_group;
   const bool has_gsrc = kGrad && (kDense || tm.grad_src != nullptr);
   const bool has_gtgt = kGrad && kLoss && (kDense || tm.grad_target != nullptr);
   const bool has_gsoft = kGrad && !kDense && (tm.grad_soft_mask != nullptr);
   const bool has_gflow = kGrad && (PARAM == DMH_PARAM_FLOW) && (kDense || tm.grad_param != nullptr);
-  float* __restrict__ out = has_out ? pin(tm.out + (size_t)b * CT * plane_o) : nullptr;
+  float* __restrict__ out = has_out ? pin(tm.out + (size_t)bv * CT * plane_o) : nullptr;
   uint8_t* __restrict__ valid = has_valid ? tm.valid + (size_t)b * plane_o : nullptr;
-  float* __restrict__ gsrc = has_gsrc ? pin(tm.grad_src + (size_t)b * CT * plane_s) : nullptr;
-  float* __restrict__ gtgt = has_gtgt ? pin(tm.grad_target + (size_t)b * CT * plane_o) : nullptr;
+  float* __restrict__ gsrc = has_gsrc ? pin(tm.grad_src + (size_t)bv * CT * plane_s) : nullptr;
+  float* __restrict__ gtgt = has_gtgt ? pin(tm.grad_target + (size_t)bv * CT * plane_o) : nullptr;
   float* __restrict__ gsoft = has_gsoft ? tm.grad_soft_mask + (size_t)b * plane_o : nullptr;
   float* __restrict__ gflow = has_gflow ? tm.grad_param + (size_t)b * 2 * plane_o : nullptr;
   const bool want_gH = kGrad && (PARAM == DMH_PARAM_HOMOGRAPHY) && (kDense || tm.grad_param != nullptr);
@@ -303,8 +307,13 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
       gcy *= r.gate_y;
       if (has_gsoft) stg_f(gsoft, po, (use_border && !r.m1) ? 0.f : gmask);
       if (has_gflow) {
-        stg_f(gflow, po, gcx);
-        stg_f(gflow, po + plane_o, gcy);
+        if (a.groups > 1) {                 // the channel groups of a sample add up (the launcher zeroed the buffer)
+          red_f(gflow, po, gcx);
+          red_f(gflow, po + plane_o, gcy);
+        } else {
+          stg_f(gflow, po, gcx);
+          stg_f(gflow, po + plane_o, gcy);
+        }
       }
       if (want_gH) {
         // flow = q/T' - g  =>  dL/dX = gcx/T', dL/dY = gcy/T', dL/dT = -(gcx*X + gcy*Y)/T'^2
@@ -435,11 +444,16 @@ int launch_pass(const FastArgs& a, int n, long long tiles, int pass, int C, int 
 int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) {
   const dmh_warp_desc& d0 = d[0];
   if (n > 2) return 1;
-  if (d0.C != 1 && d0.C != 3) return 1;
+  if (d0.C < 1) return 1;
+  // C = 1 and C = 3 are the compiled channel counts; other C run as channel groups of 3 (C % 3 == 0: the Swin pyramid
+  // levels, C = 12 / 24, HEM/model/swin_multi.py:161-166) or of 1
+  const int CT = (d0.C % 3 == 0) ? 3 : 1;
+  const int groups = d0.C / CT;
   if (d0.sampler != DMH_S1 && d0.sampler != DMH_S3_BORDER) return 1;
   if (d0.param_kind != DMH_PARAM_HOMOGRAPHY && d0.param_kind != DMH_PARAM_FLOW) return 1;
-  if ((long long)d0.C * d0.Hs * d0.Ws >= 2147483647LL || (long long)d0.C * d0.h * d0.w >= 2147483647LL) return 1;
+  if ((long long)CT * d0.Hs * d0.Ws >= 2147483647LL || (long long)CT * d0.h * d0.w >= 2147483647LL) return 1;
   FastArgs a;
+  a.groups = groups;
   const int loss = (d0.target != nullptr) ? d0.loss_form : DMH_LOSS_NONE;
   bool dense = true;
   for (int i = 0; i < n; ++i) {
@@ -450,6 +464,7 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
       dense = dense && s.use_border_mask && !s.soft_mask && s.grad_src && s.grad_target && s.grad_param &&
               !s.grad_soft_mask && !s.grad_out && (pass == PASS_BWD || s.loss_acc) && loss == DMH_LOSS_MASKED_DIFF;
     if (s.start || s.flow_out || s.indices) return 1;
+    if (groups > 1 && (s.grad_soft_mask || s.C != d0.C)) return 1;   // (dL/dsoft_mask is a plain store per sample)
     if (s.param_kind == DMH_PARAM_HOMOGRAPHY && s.divide != 1) return 1;
     if (s.loss_form != d0.loss_form || s.start_x != d0.start_x || s.start_y != d0.start_y) return 1;
     if (pass == PASS_FWD && !s.out && !s.valid && !(s.loss_form != DMH_LOSS_NONE && s.loss_acc)) return 1;
@@ -467,7 +482,7 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
   a.sx = d0.start_x; a.sy = d0.start_y;
   a.tiles_x = (d0.w + TW - 1) / TW;
   a.tiles_y = (d0.h + TH - 1) / TH;
-  const long long tiles = (long long)a.tiles_x * a.tiles_y * d0.B;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * d0.B * groups;
   if (tiles > 2147483647LL) return 1;
   // ---- the persistent TMA tile kernel takes the dense S1 homography launches (dmh_warp_tile.cu) ----
   const int tile_mode = tuning().tile;
@@ -529,13 +544,20 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
       if (rc != 1) return rc;
     }
   }
+  if (groups > 1 && pass != PASS_FWD && d0.param_kind == DMH_PARAM_FLOW) {
+    // dL/dflow of a sample is the sum over its channel groups: accumulated with REDs into a zeroed buffer
+    for (int i = 0; i < n; ++i)
+      if (d[i].grad_param &&
+          cudaMemsetAsync(d[i].grad_param, 0, (size_t)d0.B * 2 * d0.h * d0.w * sizeof(float), stream) != cudaSuccess)
+        return fail(DMH_ECUDA, "warp: cudaMemsetAsync(grad_param) failed");
+  }
   if (d0.sampler == DMH_S1) {
     if (d0.param_kind == DMH_PARAM_HOMOGRAPHY)
-      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
-    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
+      return launch_pass<DMH_S1, DMH_PARAM_HOMOGRAPHY>(a, n, tiles, pass, CT, loss, dense ? 1 : 0, stream);
+    return launch_pass<DMH_S1, DMH_PARAM_FLOW>(a, n, tiles, pass, CT, loss, dense ? 1 : 0, stream);
   }
   if (d0.param_kind == DMH_PARAM_FLOW)
-    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, d0.C, loss, dense ? 1 : 0, stream);
+    return launch_pass<DMH_S3_BORDER, DMH_PARAM_FLOW>(a, n, tiles, pass, CT, loss, dense ? 1 : 0, stream);
   return 1;
 }
 

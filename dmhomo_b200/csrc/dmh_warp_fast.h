@@ -40,6 +40,7 @@ struct FastArgs {
   int n_static, dyn_chunk, counter_slot;   // schedule: statically split prefix of the tile list, tiles per dynamic claim, counter slot
   int pair_major;               // tile list ordered (sample, term, tile) instead of (term, sample, tile)
   int interior_ok;              // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body (dmh_set_tuning "tile_interior")
+  int groups;                   // lean scalar kernel: channel groups of CT channels per sample (C = groups * CT; 1 = the whole sample)
 };
 
 // pass: 0 forward, 1 backward, 2 forward + gradients.  Returns DMH_OK / DMH_ECUDA when it

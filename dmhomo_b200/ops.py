@@ -396,7 +396,7 @@ def warp(img, param, kind=PARAM_FLOW, sampler=S1, out_hw=None, start=0, basis=No
     out, extras = res[0], list(res[1:])
     ret = [out]
     if return_mask:
-        ret.append(extras.pop(0).bool())
+        ret.append(extras.pop(0).view(torch.bool))      # the kernels write exactly 0 / 1: reinterpret, no copy
     if return_flow:
         ret.append(extras.pop(0))
     if return_indices:
@@ -640,7 +640,7 @@ def warp_eval(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DI
         sw_ptrs = (C.c_void_p * n)(*[_p(t[4]) for t in tl])
         with torch.cuda.device(dev):
             L.check(L.lib().dmh_loss_finish(acc_ptrs, sw_ptrs, n, B, scale, _p(loss), _stream(dev)), "loss_finish")
-    return loss, outs, ([v.bool() for v in valids] if masks_as_bool else valids)
+    return loss, outs, ([v.view(torch.bool) for v in valids] if masks_as_bool else valids)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -784,7 +784,7 @@ def border_mask(flow, as_float=False):
         a, b = _p(out), None
     with torch.cuda.device(dev):
         L.check(L.lib().dmh_border_mask(_p(f), a, b, B, h, w, _stream(dev)), "border_mask")
-    return out if as_float else out.bool()
+    return out if as_float else out.view(torch.bool)    # 0 / 1 bytes reinterpreted, no copy
 
 
 def zero_border_mask(image, eps=1e-6):
@@ -797,7 +797,7 @@ def zero_border_mask(image, eps=1e-6):
     out = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
         L.check(L.lib().dmh_zero_border_mask(_p(im), _p(out), B, h, w, float(eps), _stream(dev)), "zero_border_mask")
-    return out.bool()
+    return out.view(torch.bool)
 
 
 class _L1(torch.autograd.Function):

@@ -7,6 +7,8 @@ have a closed form that plain torch ops on the GPU can state at any size - no or
     M1 mask            = 0 <= x + tx <= W and 0 <= y + ty <= H                      (flow_and_mapping_operations.py:66-69)
     loss               = mean |m * target - m * warp|, its gradients by autograd through the same closed form.
 """
+import os
+
 import pytest
 import torch
 
@@ -96,6 +98,8 @@ def _check_against_fp64(name, cuda, ref32, ref64):
     """|cuda - fp64| <= max(1e-4, |oracle_fp32 - fp64|), elementwise maxima."""
     e_cuda = (cuda.double().cpu() - ref64).abs().max().item()
     e_ref = (ref32.double() - ref64).abs().max().item()
+    if os.environ.get("DMH_TEST_REPORT"):
+        print(f"[margin] {name}: cuda {e_cuda:.3e} oracle {e_ref:.3e} bound {max(ATOL, 1.05 * e_ref):.3e}")
     assert e_cuda <= max(ATOL, 1.05 * e_ref), f"{name}: |cuda - fp64| = {e_cuda:.3e}, |oracle fp32 - fp64| = {e_ref:.3e}"
 
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from dmhomo_b200 import ops
-from dmhomo_b200.compat import data_loader as cdl, hem_utils
+from dmhomo_b200.compat import data_loader as cdl, dgm, hem_utils
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -129,6 +129,39 @@ def test_pyramid_level_feature_warp(C):
     assert (out_g.detach().cpu() - out_c.detach()).abs().max().item() < 1e-4
     assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4
     assert ((wg.grad.cpu() - wc.grad).norm() / wc.grad.norm()).item() < 1e-3
+
+
+@pytest.mark.parametrize("C", [2, 6, 7, 12])
+def test_multichannel_flow_warp_channel_groups(C):
+    """Feature maps with C other than 1 / 3 run on the lean kernel as channel groups of 3 (C % 3 == 0) or 1: pixels
+    bit-exact against get_warp_flow (HEM/model/utils.py:443-553), dL/dfeat and dL/dflow (summed over the groups of a
+    sample) within 1e-4; the S3 sampler (DGM flow_warp) through the same grouping."""
+    B, h, w = 3, 40, 72
+    feat = torch.randn(B, C, h, w, generator=g(91))
+    flow = torch.randn(B, 2, h, w, generator=g(92)) * 5
+    go = torch.randn(B, C, h, w, generator=g(93))
+    fc, lc = feat.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    out_c = port.get_warp_flow(fc, lc)
+    out_c.backward(go)
+    fg, lg = feat.clone().to(DEV).requires_grad_(True), flow.clone().to(DEV).requires_grad_(True)
+    out_g = hem_utils.get_warp_flow(fg, lg)
+    out_g.backward(go.to(DEV))
+    assert torch.equal(out_g.detach().cpu(), out_c.detach())
+    assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4
+    scale = max(1.0, lc.grad.abs().max().item())
+    assert ((lg.grad.cpu() - lc.grad).abs().max().item() / scale) < 1e-4
+    # mask + S3
+    out_m, mask = ops.warp(feat.to(DEV), flow.to(DEV), kind=ops.PARAM_FLOW, return_mask=True)
+    assert torch.equal(out_m.cpu(), out_c.detach()) and torch.equal(mask.cpu(), port.correspondence_mask(flow))
+    f3, l3 = feat.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    o3 = port.flow_warp(f3, l3)
+    o3.backward(go)
+    g3, m3 = feat.clone().to(DEV).requires_grad_(True), flow.clone().to(DEV).requires_grad_(True)
+    og = dgm.flow_warp(g3, m3)
+    og.backward(go.to(DEV))
+    assert (og.detach().cpu() - o3.detach()).abs().max().item() < 1e-4
+    assert (g3.grad.cpu() - f3.grad).abs().max().item() < 1e-4
+    assert ((m3.grad.cpu() - l3.grad).abs().max().item() / max(1.0, l3.grad.abs().max().item())) < 1e-4
 
 
 # ---------------------------------------------------------------------------------- remaining helpers of the module files

@@ -266,6 +266,23 @@ def _flows(B, h, w, seed):
     return {"smooth": smooth, "noisy": noisy, "wild": wild}
 
 
+def _scatter_mass(flow, gout, Hs, Ws):
+    """Sum of |bilinear weight| * |upstream gradient| over every tap that lands on a source pixel (S1 taps and weights
+    as in HEM/model/utils.py:463-523, fp64): the magnitude scale of the scattered sum dL/dimg, (B,1,Hs,Ws)."""
+    B, _, h, w = flow.shape
+    c = port.pixel_grid(B, h, w)[:, :2].double() + flow.double()
+    x, y = c[:, 0].reshape(-1), c[:, 1].reshape(-1)
+    x0, y0 = torch.floor(x), torch.floor(y)
+    x1, y1 = (x0 + 1).clamp(0, Ws - 1), (y0 + 1).clamp(0, Hs - 1)
+    x0, y0 = x0.clamp(0, Ws - 1), y0.clamp(0, Hs - 1)
+    base = (torch.arange(B) * (Hs * Ws)).repeat_interleave(h * w)
+    ga = gout.double().abs().sum(1).reshape(-1)
+    m = torch.zeros(B * Hs * Ws, dtype=torch.float64)
+    for xi, yi, wt in ((x0, y0, (x1 - x) * (y1 - y)), (x0, y1, (x1 - x) * (y - y0)), (x1, y0, (x - x0) * (y1 - y)), (x1, y1, (x - x0) * (y - y0))):
+        m.index_add_(0, base + yi.long() * Ws + xi.long(), wt.abs() * ga)
+    return m.reshape(B, 1, Hs, Ws)
+
+
 @pytest.mark.parametrize("kind", ["smooth", "noisy", "wild"])
 def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
     from dmhomo_b200 import _lib
@@ -282,7 +299,11 @@ def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
     # is noise there.  Yardstick: the same pipeline in fp64; the kernels must be as close to it as the fp32 oracle is.
     i64, f64 = img.double().requires_grad_(True), flow.double().requires_grad_(True)
     (port.get_warp_flow(i64, f64) * gout.double()).sum().backward()
-    img_tol = max(1e-4, 4.0 * (ic.grad.double() - i64.grad).abs().max().item())
+    # ... within one fp32 ulp of the MASS of the sum (sum of |weight * upstream gradient| over the taps that land on a
+    # pixel: 1.6e6 at the corner pixel of the wild case, where the fp32 oracle itself is off by 4e-3), or 1e-4.
+    # The order of the atomic adds differs from run to run, so a multiple of the oracle's own error is no stable bound.
+    img_tol = 1e-4 + _scatter_mass(flow, gout, h, w) * 2.0 ** -24
+    assert ((ic.grad.double() - i64.grad).abs() <= img_tol).all()      # the yardstick holds for the reference's own fp32
 
     res = {}
     for tile_flow in (1, 0):
@@ -298,16 +319,16 @@ def test_tile_flow_forward_backward_against_oracle_and_scalar_kernel(kind):
         assert ("tile" in kern_f) == bool(tile_flow) and ("tile" in kern_b) == bool(tile_flow), (kern_f, kern_b)
         assert torch.equal(out.detach().cpu(), ref.detach()), "warped pixels differ from the oracle"
         assert (ig.grad.cpu()[..., 1:-1, 1:-1] - ic.grad[..., 1:-1, 1:-1]).abs().max().item() < 1e-4
-        assert (ig.grad.cpu().double() - i64.grad).abs().max().item() < img_tol
+        assert ((ig.grad.cpu().double() - i64.grad).abs() <= img_tol).all()
         assert (fg.grad.cpu() - fc.grad).abs().max().item() < 1e-4 * max(1.0, fc.grad.abs().max().item())
         res[tile_flow] = (out.detach(), ig.grad, fg.grad)
     assert torch.equal(res[1][2], res[0][2]), "dL/dflow differs between the tile and the scalar kernel"
-    assert (res[1][1] - res[0][1]).abs().max().item() < 2 * img_tol      # scattered sums: order differs
+    assert ((res[1][1] - res[0][1]).abs().cpu().double() <= 2 * img_tol).all()      # scattered sums: order differs
 
     # only one of the two gradients wanted
     ig = img.to(DEV).requires_grad_(True)
     (hem_utils.get_warp_flow(ig, flow.to(DEV)) * gout.to(DEV)).sum().backward()
-    assert (ig.grad - res[1][1]).abs().max().item() < 2 * img_tol
+    assert ((ig.grad - res[1][1]).abs().cpu().double() <= 2 * img_tol).all()
     fg = flow.to(DEV).requires_grad_(True)
     (hem_utils.get_warp_flow(img.to(DEV), fg) * gout.to(DEV)).sum().backward()
     assert torch.equal(fg.grad, res[1][2])
