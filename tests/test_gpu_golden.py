@@ -76,6 +76,49 @@ def test_pipeline_golden():
     assert rel_fro(ops.dlt4(src, src + d["off_f"].to(DEV)).cpu(), d["Hf"]) < 1e-5
 
 
+def test_pipeline_basis_golden_through_the_reference_names():
+    """cfg 2 as the reference's own statements issue it (tests/golden/make_golden.py: gen_basis -> basis product ->
+    corner offsets -> DLT -> get_flow -> get_warp_flow x2 -> create_border_mask x2 -> LossL1 x2 -> backward), run here
+    through the names compat.patch_reference() installs, against what the reference produced; then the fused op on the
+    same inputs."""
+    d = load("pipeline_basis")
+    h, w = [int(v) for v in d["hw"]]
+    B = d["img1"].shape[0]
+    basis = hem_utils.gen_basis(h, w).to(DEV)
+    leaves = [d[k].clone().to(DEV).requires_grad_(True) for k in ("img1", "img2", "w_f", "w_b")]
+    c1, c2, wf, wb = leaves
+    src = torch.tensor([[0, 0], [w - 1, 0], [0, h - 1], [w - 1, h - 1]], dtype=torch.float32, device=DEV).repeat(B, 1, 1)
+
+    def corner_offsets(wt):
+        fl = (basis.reshape(1, 8, -1) * wt).sum(1).reshape(B, 2, h, w)          # net.py:808-809, inline torch in the reference
+        return torch.stack([fl[:, :, 0, 0], fl[:, :, 0, w - 1], fl[:, :, h - 1, 0], fl[:, :, h - 1, w - 1]], 1)
+
+    Hf, Hb = hem_utils.DLT(B)(src, src + corner_offsets(wf)), hem_utils.DLT(B)(src, src + corner_offsets(wb))
+    grid = hem_utils.get_grid(B, h, w, 0)
+    ff, _ = hem_utils.get_flow(Hf.view(B, 1, 3, 3), grid, h, w, 1)
+    fb, _ = hem_utils.get_flow(Hb.view(B, 1, 3, 3), grid, h, w, 1)
+    w2, w1 = hem_utils.get_warp_flow(c2, ff), hem_utils.get_warp_flow(c1, fb)
+    mf, mb = fmo.create_border_mask(ff).unsqueeze(1), fmo.create_border_mask(fb).unsqueeze(1)
+    l1 = losses.LossL1(reduction="mean")
+    loss = l1(mf * c1, mf * w2) + l1(mb * c2, mb * w1)
+    loss.backward()
+    assert rel_fro(Hf.detach().cpu(), d["Hf"]) < 1e-5 and rel_fro(Hb.detach().cpu(), d["Hb"]) < 1e-5
+    assert (ff.detach().cpu() - d["flow_f"]).abs().max().item() < ATOL and (fb.detach().cpu() - d["flow_b"]).abs().max().item() < ATOL
+    assert (w2.detach().cpu() - d["w2"]).abs().max().item() < ATOL and (w1.detach().cpu() - d["w1"]).abs().max().item() < ATOL
+    assert abs(loss.item() - d["loss"].item()) < 1e-5
+    assert (c1.grad.cpu() - d["g_img1"]).abs().max().item() < ATOL and (c2.grad.cpu() - d["g_img2"]).abs().max().item() < ATOL
+    assert rel_fro(wf.grad.cpu(), d["g_wf"]) < 1e-3 and rel_fro(wb.grad.cpu(), d["g_wb"]) < 1e-3
+
+    # the same step as ONE op (basis -> H -> both warps + masks + L1 + every gradient in one launch chain)
+    f1, f2, fwf, fwb = [d[k].clone().to(DEV).requires_grad_(True) for k in ("img1", "img2", "w_f", "w_b")]
+    floss, fHf, fHb = ops.basis_warp_loss(basis, f1, f2, fwf, fwb, return_homographies=True)
+    floss.backward()
+    assert rel_fro(fHf.cpu(), d["Hf"]) < 1e-5 and rel_fro(fHb.cpu(), d["Hb"]) < 1e-5
+    assert abs(floss.item() - d["loss"].item()) < 1e-5
+    assert (f1.grad.cpu() - d["g_img1"]).abs().max().item() < ATOL and (f2.grad.cpu() - d["g_img2"]).abs().max().item() < ATOL
+    assert rel_fro(fwf.grad.cpu().reshape(B, 8, 1), d["g_wf"]) < 1e-3 and rel_fro(fwb.grad.cpu().reshape(B, 8, 1), d["g_wb"]) < 1e-3
+
+
 def test_warp_images_golden():
     d = load("warp_images")
     out, flow = hem_utils.WarpImages(d["img"].to(DEV), d["H"].to(DEV), d["start"].to(DEV), tuple(int(v) for v in d["patch_wh"]))
