@@ -341,9 +341,10 @@ def _pipeline_inputs(B, C, h, w, rho, seed, smooth):
 
 
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("C", [1, 3])
+@pytest.mark.parametrize("C", [1, 3, 4, 6])
 def test_fused_bidirectional_loss_stage_isolated(fused, C):
-    """Oracle H fed to both sides (stage isolation, noise images): loss + gradients to both images and H."""
+    """Oracle H fed to both sides (stage isolation, noise images): loss + gradients to both images and H.  C = 4 / 6:
+    feature maps, walked as channel groups of 1 / 3 whose loss and dL/dH sums add up per sample."""
     B, h, w = 4, 72, 128
     img1, img2, off_f, off_b = _pipeline_inputs(B, C, h, w, 8.0, 40, smooth=False)
     src = port.corner_points(B, h, w)
@@ -393,9 +394,11 @@ def test_fused_loss_upstream_scaling_and_weight():
         assert (grad - i2c.grad).abs().max().item() < 1e-6
 
 
-def test_fused_loss_soft_mask_and_flow_param():
-    """OSNet's 'unsup' term: soft masks from the mask net, warp by an explicit flow, grads to flow and masks."""
-    B, C, h, w = 2, 1, 32, 48
+@pytest.mark.parametrize("C", [1, 6])
+def test_fused_loss_soft_mask_and_flow_param(C):
+    """OSNet's 'unsup' term: soft masks from the mask net, warp by an explicit flow, grads to flow and masks
+    (C = 6: feature maps, net.py:817-818 warps img2_fea)."""
+    B, h, w = 2, 32, 48
     gen = g(42)
     f1, f2 = synth.smooth_images(B, C, h, w, gen), synth.smooth_images(B, C, h, w, gen)
     flow_f = torch.randn(B, 2, h, w, generator=gen) * 3
