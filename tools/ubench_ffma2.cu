@@ -82,9 +82,9 @@ template <int MODE>
 void run(const char* name, float* o, long long* cyc) {
   const int iters = 20000;
   printf("%-44s", name);
-  for (int wps = 1; wps <= 8; wps *= 2) {      // warps per sub-partition: one CTA per SM of 4 * wps warps
+  for (int wps = 1; wps <= 8; wps *= 2) {      // warps per sub-partition: one CTA per SM of 4 * wps warps (8: only the modes with few registers launch)
     k<MODE><<<148, 128 * wps>>>(o, iters, 1.0000001f, 1e-6f, cyc);
-    cudaDeviceSynchronize();
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("  %dw: launch failed", wps); continue; }
     long long c;
     cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
     const double instr_per_smsp = (double)iters * N * wps * ((MODE == 5) ? 2 : 1);
