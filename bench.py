@@ -915,6 +915,24 @@ def run_e2e(ctx, st, m, K):
     copy_done = [torch.cuda.Event() for _ in range(n_sets)]
     gen = torch.Generator().manual_seed(1234 + ctx.rank)
     results = {}
+    # what the host link of THIS box gives a plain pinned copy of one step's uint8 input (max over ranks of the time, all
+    # ranks copying at once): the ceiling of the end-to-end number, reported next to it
+    probe_host = torch.empty(2 * B * C * h * w, dtype=torch.uint8).pin_memory()
+    probe_dev = torch.empty_like(probe_host, device=dev)
+    with torch.cuda.stream(copy_stream):
+        for _ in range(60):               # an idle PCIe link needs tens of milliseconds of traffic to come back to full speed
+            probe_dev.copy_(probe_host, non_blocking=True)
+        copy_stream.synchronize()
+        ctx.barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(copy_stream)
+        for _ in range(20):
+            probe_dev.copy_(probe_host, non_blocking=True)
+        p1.record(copy_stream)
+        copy_stream.synchronize()
+    (probe_ms,) = ctx.max_over_ranks([p0.elapsed_time(p1) / 20])
+    link_gbs = probe_host.numel() / (probe_ms * 1e-3) / 1e9
+    del probe_host, probe_dev
     with torch.cuda.stream(stream):
         par_host = [tuple(t.detach().cpu().pin_memory() for t in st.sets[k][2:]) for k in range(n_sets)]
         formats = ["u8_gray_patches", "fp32_gray_patches"]
@@ -979,7 +997,7 @@ def run_e2e(ctx, st, m, K):
                 copy_stream.synchronize()
                 return last
 
-            e2e_loop(2)
+            e2e_loop(20)                  # warm-up: buffers touched, link at full speed
             ctx.barrier()
             t0 = time.perf_counter()
             e2e_loop(Ke)
@@ -987,7 +1005,8 @@ def run_e2e(ctx, st, m, K):
             ctx.barrier()
             (sec,) = ctx.max_over_ranks([time.perf_counter() - t0])
             results[fmt] = {"value": st.pixels * ctx.world * Ke / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                            "d2h_bytes_per_step": 4, "steps": Ke}
+                            "d2h_bytes_per_step": 4, "steps": Ke, "h2d_gbs_achieved": h2d * Ke / sec / 1e9,
+                            "h2d_gbs_plain_copy_slowest_rank": link_gbs}
             del host, staging
     return results
 
