@@ -126,3 +126,12 @@ def split_sample_batches(buf):
         for i in range(len(imgs)):
             out.append({"img12": imgs[i], "homo12": homos[i]})
     return out
+
+
+def render_conditions(img2s, homos, max_flow=256):
+    """The condition images a DGM sampling step derives from (img2s, condition homographies): postProcess_cv2's
+    warpPerspective (ddpm.py:1520-1529), homo_to_flow + visulize_flow (ddpm.py:972-975, 1489-1502) and postProcess's
+    flow_warp (ddpm.py:1505-1518), as ONE call whose independent launches overlap (ops.render_conditions).  Tensors in,
+    dict of tensors out; every entry is bit-identical to the separate call of the same name."""
+    return ops.render_conditions(img2s, homos, max_flow=max_flow)
+

@@ -13,7 +13,7 @@ from ._lib import (LOSS_DIFF_MASKED, LOSS_MASKED_DIFF, LOSS_NONE, PARAM_BASIS8, 
                    PARAM_HOMOGRAPHY, S1, S1B, S2_ZEROS, S3_BORDER)
 
 __all__ = [
-    "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8",
+    "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8", "render_conditions",
     "LOSS_NONE", "LOSS_MASKED_DIFF", "LOSS_DIFF_MASKED", "dlt4", "homography_to_flow", "homography_to_flow_f64",
     "basis_combine", "basis_corner_offsets", "basis_homography", "warp", "warp_into", "warp_loss", "warp_eval", "WarpTerm", "u8_to_f32", "pairs_u8_to_gray", "border_mask", "zero_border_mask",
     "l1_loss", "flow_to_rgb", "warp_perspective", "eval_point_error", "flow_to_homography_ls",
@@ -649,9 +649,9 @@ def warp_eval(terms, kind=PARAM_HOMOGRAPHY, sampler=S1, loss_form=LOSS_MASKED_DI
 _side_streams = {}
 
 
-def _side_stream(dev):
-    """One auxiliary stream per device for the short fork / join branches of basis_warp_loss."""
-    key = (dev.type, dev.index)
+def _side_stream(dev, idx=0):
+    """Auxiliary streams per device for the short fork / join branches of basis_warp_loss and render_conditions."""
+    key = (dev.type, dev.index, idx)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(dev)
     return _side_streams[key]
@@ -880,6 +880,55 @@ def warp_perspective(img, H, dsize, channels_last=False):
     with torch.cuda.device(dev):
         L.check(fn(_p(im), _p(Hc), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last), _stream(dev)), "warp_perspective")
     return out
+
+
+def render_conditions(im2, homo, max_flow=256.0, timing_events=None):
+    """Everything the DGM condition rendering derives from one batch (im2 (B,3,h,w) in [0,1], condition homographies
+    (B,3,3) at that resolution) in one call: cv2.warpPerspective(im2, homo) (postProcess_cv2, ddpm.py:1520-1529), the
+    fp64 homography flow (homo_to_flow, ddpm.py:913-975), its colour wheel image (flow_to_image, ddpm.py:1471-1502) and
+    flow_warp(im2, flow) (postProcess, ddpm.py:1505-1518).  The four launches are the same kernels the separate calls
+    use; here the independent ones sit on forked stream branches (parallel nodes once captured into a CUDA graph):
+
+        warpPerspective                 ||  homography -> flow  ->  flow_warp (S3)
+                                        ||                      ->  flow -> RGB
+
+    Returns {"warp": (B,3,h,w), "flow": (B,2,h,w), "flow_rgb": (B,3,h,w), "flow_warp": (B,3,h,w)}.  No autograd.
+    timing_events: optional (begin, end) events recorded around the warpPerspective launch on its own stream."""
+    dev = _cuda(im2, homo)
+    im = _f32(im2)
+    Hc = homo.to(torch.float64).contiguous()
+    B, Cc, h, w = im.shape
+    if Hc.numel() != B * 9:
+        raise ValueError("render_conditions: homo must be (B,3,3)")
+    lib = L.lib()
+    cur, s_a, s_b = torch.cuda.current_stream(dev), _side_stream(dev, 0), _side_stream(dev, 1)
+    with torch.cuda.device(dev), torch.no_grad():
+        warp_out = torch.empty(B, Cc, h, w, device=dev, dtype=torch.float32)      # every output belongs to the caller's stream
+        flow = torch.empty(B, 2, h, w, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, 3, h, w, device=dev, dtype=torch.float32)
+        fwarp = torch.empty(B, Cc, h, w, device=dev, dtype=torch.float32)
+        fork, have_flow, join_a, join_b = (torch.cuda.Event() for _ in range(4))
+        fork.record(cur)
+        s_a.wait_event(fork)
+        with torch.cuda.stream(s_a):
+            if timing_events is not None:
+                timing_events[0].record(s_a)
+            L.check(lib.dmh_warp_perspective(_p(im), _p(Hc), _p(warp_out), B, Cc, h, w, h, w, 0, C.c_void_p(s_a.cuda_stream)),
+                    "warp_perspective")
+            if timing_events is not None:
+                timing_events[1].record(s_a)
+            join_a.record(s_a)
+        L.check(lib.dmh_homography_to_flow_f64(_p(Hc), _p(flow), B, h, w, 1e-6, 0, 0, _stream(dev)), "homography_to_flow_f64")
+        have_flow.record(cur)
+        s_b.wait_event(have_flow)
+        with torch.cuda.stream(s_b):
+            L.check(lib.dmh_flow_to_rgb(_p(flow), _p(rgb), B, h, w, max(float(max_flow), 1.0), 0, 0, C.c_void_p(s_b.cuda_stream)),
+                    "flow_to_rgb")
+            join_b.record(s_b)
+        warp_into(im, flow, fwarp, kind=PARAM_FLOW, sampler=S3_BORDER)
+        cur.wait_event(join_a)
+        cur.wait_event(join_b)
+    return {"warp": warp_out, "flow": flow, "flow_rgb": rgb, "flow_warp": fwarp}
 
 
 def eval_point_error(pts, flow_f, flow_b):

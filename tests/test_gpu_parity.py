@@ -646,6 +646,37 @@ def test_cfg3_dgm_render():
     assert (fw - ref["flow_warp"]).abs().max().item() < ATOL
 
 
+def test_render_conditions_one_call_equals_the_separate_calls():
+    """ops.render_conditions (forked stream branches) against the four separate calls, eagerly and replayed from a CUDA
+    graph: bit-identical outputs."""
+    B, h, w = 5, 64, 96
+    gen = g(310)
+    im2 = torch.rand(B, 3, h, w, generator=gen).to(DEV)
+    H360 = synth.homographies_360x640(B, gen, 24.0)
+    homo = torch.stack([torch.from_numpy(dgm.adapt_homography_to_preprocessing_v3(360, 640, H360[b], h, w)) for b in range(B)]).to(DEV)
+    ref_warp = ops.warp_perspective(im2, homo, (w, h))
+    ref_flow = ops.homography_to_flow_f64(homo, h, w, eps=1e-6, channels_last=False)
+    ref_rgb = ops.flow_to_rgb(ref_flow, 256.0)
+    ref_fw = dgm.flow_warp(im2, ref_flow)
+    out = dgm.render_conditions(im2, homo)
+    torch.cuda.synchronize()
+    for key, ref in (("warp", ref_warp), ("flow", ref_flow), ("flow_rgb", ref_rgb), ("flow_warp", ref_fw)):
+        assert torch.equal(out[key], ref), key
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        dgm.render_conditions(im2, homo)
+        stream.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            captured = dgm.render_conditions(im2, homo)
+        for t in captured.values():
+            t.zero_()
+        gr.replay()
+        stream.synchronize()
+    for key, ref in (("warp", ref_warp), ("flow", ref_flow), ("flow_rgb", ref_rgb), ("flow_warp", ref_fw)):
+        assert torch.equal(captured[key], ref), key
+
+
 def test_post_process():
     B, h = 2, 256
     gen = g(52)
