@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) basis_combine_kernel(const float* __
 }
 
 // Four pixels per thread (plane % 4 == 0): 128-bit loads and stores, same per-pixel operation order.
-__global__ void __launch_bounds__(kThreads, 2) basis_combine4_kernel(const float* __restrict__ basis,
+__global__ void __launch_bounds__(kThreads, 3) basis_combine4_kernel(const float* __restrict__ basis,
                                                                      const float* __restrict__ weight,
                                                                      float* __restrict__ flow, int B, long long plane4,
                                                                      int b_per_block) {
