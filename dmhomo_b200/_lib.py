@@ -96,6 +96,8 @@ SIGNATURES = {
     "dmh_flow_to_rgb": [_fp, _fp, _i, _i, _i, _f, _i, _i, _fp],
     "dmh_warp_perspective": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_warp_perspective_u8": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
+    "dmh_remap": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp],
+    "dmh_remap_u8": [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp],
     "dmh_eval_point_error": [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp],
     "dmh_flow_to_homography_ls": [_fp, _fp, _fp, _i, _i, _i, _fp],
     "dmh_pairs_u8_to_gray": [_fp, _fp, _fp, _fp, _fp, C.POINTER(_d), C.POINTER(_d), _i, _i, _i, _i, _i, _i, _fp],

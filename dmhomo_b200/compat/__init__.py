@@ -17,7 +17,9 @@ from . import data_loader, dgm, flow_and_mapping_operations, hem_net, hem_utils,
 _TARGETS = {
     "model.utils": (hem_utils, hem_utils.__all__),
     "model.net": (hem_net, ["DLT_solve"]),
-    "utils_operations.pixel_wise_mapping": (pixel_wise_mapping, pixel_wise_mapping.__all__),
+    # (remap_using_* are host-side numpy helpers of the loaders' augmentation, flow_and_mapping_operations.py:74-81: left
+    #  alone like every loader-side helper; their GPU forms are importable from compat.pixel_wise_mapping)
+    "utils_operations.pixel_wise_mapping": (pixel_wise_mapping, ["warp", "warp_with_mapping"]),
     "utils_operations.flow_and_mapping_operations": (flow_and_mapping_operations,
                                                      ["get_gt_correspondence_mask", "create_border_mask",
                                                       "from_homography_to_pixel_wise_mapping"]),

@@ -32,16 +32,20 @@ __device__ __forceinline__ bool invert3(const double* s, double* t) {
 //   uint8 images:   OpenCV's fixed-point remap - the same table scaled to 2^15 (exact integers at 1/32 steps),
 //                   (sum w_i p_i + 2^14) >> 15; bit-identical to cv2 on uint8 (tests/test_oracle_golden.py).
 // The inverse of H is taken once per CTA (one fp64 division instead of one per thread).
-template <typename T>
+// MAP: cv2.remap(src, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT) instead - the source coordinates come from a
+// (B,2,h,w) fp32 tensor `map` (absolute coordinates; disp != 0: displacements, the pixel grid is added in fp32, which is
+// the reference's fp64 sum rounded to fp32) and are fixed to 1/32 px by cvRound(v * 32) (convertMaps / remap, round
+// half to even, out of range -> INT_MIN as cvtss2si gives it), the integer part saturated to int16 as OpenCV stores it.
+template <typename T, bool MAP>
 __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ src, const double* __restrict__ H,
-                                                         T* __restrict__ dst, int B, int C, int Hs, int Ws, int h,
-                                                         int w, int cl, int bw0) {
+                                                         const float* __restrict__ map, int disp, T* __restrict__ dst, int B,
+                                                         int C, int Hs, int Ws, int h, int w, int cl, int bw0) {
   constexpr bool kU8 = sizeof(T) == 1;
   const int b = blockIdx.z;
   const int x = blockIdx.x * 64 + (threadIdx.x & 63);
   const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
   __shared__ double Ms[9];
-  if (threadIdx.x == 0) {
+  if (!MAP && threadIdx.x == 0) {
     double Hm[9], Mi[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Hm[k] = __ldg(H + (size_t)b * 9 + k);
@@ -52,8 +56,22 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ s
 #pragma unroll
     for (int k = 0; k < 9; ++k) Ms[k] = Mi[k];
   }
-  __syncthreads();
+  if (!MAP) __syncthreads();
   if (x >= w || y >= h) return;
+  int X, Y, sx, sy;
+  if (MAP) {
+    const size_t po = (size_t)b * 2 * h * w + (size_t)y * w + x;
+    float mx = __ldg(map + po), my = __ldg(map + po + (size_t)h * w);
+    if (disp) {
+      mx = add_rn((float)x, mx);
+      my = add_rn((float)y, my);
+    }
+    const float fx32 = mul_rn(mx, 32.0f), fy32 = mul_rn(my, 32.0f);
+    X = (fabsf(fx32) < 2147483648.0f) ? __float2int_rn(fx32) : (int)0x80000000;    // (NaN compares false)
+    Y = (fabsf(fy32) < 2147483648.0f) ? __float2int_rn(fy32) : (int)0x80000000;
+    sx = min(max(X >> 5, -32768), 32767);
+    sy = min(max(Y >> 5, -32768), 32767);
+  } else {
   double M[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) M[k] = Ms[k];
@@ -67,8 +85,11 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ s
   const double lo = -2147483648.0, hi = 2147483647.0;
   const double fX = fmax(lo, fmin(hi, __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), Wd)));
   const double fY = fmax(lo, fmin(hi, __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), Wd)));
-  const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
-  const int sx = X >> 5, sy = Y >> 5;
+  X = __double2int_rn(fX);
+  Y = __double2int_rn(fY);
+  sx = X >> 5;
+  sy = Y >> 5;
+  }
   const int iax = X & 31, iay = Y & 31;
   const float ax = div_rn((float)iax, 32.0f), ay = div_rn((float)iay, 32.0f);
   const float bx0 = sub_rn(1.0f, ax), by0 = sub_rn(1.0f, ay);
@@ -250,10 +271,32 @@ int warp_perspective_launch(const T* src, const double* H, T* dst, int B, int C,
   int bw0 = 1024 / bh0;
   bw0 = bw0 < w ? bw0 : w;
   dim3 grid((unsigned)((w + 63) / 64), (unsigned)((h + 3) / 4), (unsigned)B);
-  warp_persp_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(src, H, dst, B, C, Hs, Ws, h, w, channels_last, bw0);
+  warp_persp_kernel<T, false><<<grid, 256, 0, as_stream(stream)>>>(src, H, nullptr, 0, dst, B, C, Hs, Ws, h, w, channels_last, bw0);
   return launched("warp_persp_kernel");
 }
+
+template <typename T>
+int remap_launch(const T* src, const float* map, T* dst, int B, int C, int Hs, int Ws, int h, int w, int channels_last,
+                 int displacement, void* stream) {
+  DMH_REQUIRE(src && map && dst, "remap: null pointer");
+  DMH_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hs > 0 && Ws > 0 && h > 0 && w > 0, "remap: bad size");
+  DMH_REQUIRE((long long)Hs * Ws * C < 2147483647LL && (long long)h * w * C < 2147483647LL, "remap: image too large");
+  dim3 grid((unsigned)((w + 63) / 64), (unsigned)((h + 3) / 4), (unsigned)B);
+  warp_persp_kernel<T, true><<<grid, 256, 0, as_stream(stream)>>>(src, nullptr, map, displacement, dst, B, C, Hs, Ws, h, w,
+                                                                  channels_last, 1);
+  return launched("remap_kernel");
+}
 }  // namespace
+
+extern "C" int dmh_remap(const float* src, const float* map, float* dst, int B, int C, int Hs, int Ws, int h, int w,
+                         int channels_last, int displacement, void* stream) {
+  return remap_launch<float>(src, map, dst, B, C, Hs, Ws, h, w, channels_last, displacement, stream);
+}
+
+extern "C" int dmh_remap_u8(const uint8_t* src, const float* map, uint8_t* dst, int B, int C, int Hs, int Ws, int h, int w,
+                            int channels_last, int displacement, void* stream) {
+  return remap_launch<uint8_t>(src, map, dst, B, C, Hs, Ws, h, w, channels_last, displacement, stream);
+}
 
 extern "C" int dmh_warp_perspective(const float* src, const double* H, float* dst, int B, int C, int Hs, int Ws, int h,
                                     int w, int channels_last, void* stream) {

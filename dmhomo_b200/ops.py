@@ -13,7 +13,7 @@ from ._lib import (LOSS_DIFF_MASKED, LOSS_MASKED_DIFF, LOSS_NONE, PARAM_BASIS8, 
                    PARAM_HOMOGRAPHY, S1, S1B, S2_ZEROS, S3_BORDER)
 
 __all__ = [
-    "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8", "render_conditions",
+    "S1", "S1B", "S2_ZEROS", "S3_BORDER", "PARAM_FLOW", "PARAM_COORDS", "PARAM_HOMOGRAPHY", "PARAM_BASIS8", "render_conditions", "remap",
     "LOSS_NONE", "LOSS_MASKED_DIFF", "LOSS_DIFF_MASKED", "dlt4", "homography_to_flow", "homography_to_flow_f64",
     "basis_combine", "basis_corner_offsets", "basis_homography", "warp", "warp_into", "warp_loss", "warp_eval", "WarpTerm", "u8_to_f32", "pairs_u8_to_gray", "border_mask", "zero_border_mask",
     "l1_loss", "flow_to_rgb", "warp_perspective", "eval_point_error", "flow_to_homography_ls",
@@ -879,6 +879,28 @@ def warp_perspective(img, H, dsize, channels_last=False):
     fn = L.lib().dmh_warp_perspective_u8 if u8 else L.lib().dmh_warp_perspective
     with torch.cuda.device(dev):
         L.check(fn(_p(im), _p(Hc), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last), _stream(dev)), "warp_perspective")
+    return out
+
+
+def remap(img, coords, displacement=False, channels_last=False):
+    """cv2.remap(img, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT), batched (pixel_wise_mapping.py:7-52): img
+    (B,C,Hs,Ws) [or (B,Hs,Ws,C)] fp32 or uint8, coords (B,2,h,w) fp32 absolute source coordinates (x, y) - or
+    displacements to the pixel grid with displacement=True.  Bit-identical to OpenCV (1/32 px fixed-point coordinates)."""
+    dev = _cuda(img, coords)
+    u8 = img.dtype == torch.uint8
+    im = img.contiguous() if u8 else _f32(img)
+    mp = _f32(coords)
+    if channels_last:
+        B, Hs, Ws, Cc = im.shape
+    else:
+        B, Cc, Hs, Ws = im.shape
+    if mp.dim() != 4 or mp.shape[0] != B or mp.shape[1] != 2:
+        raise ValueError("remap: coords must be (B,2,h,w)")
+    h, w = int(mp.shape[2]), int(mp.shape[3])
+    out = torch.empty((B, h, w, Cc) if channels_last else (B, Cc, h, w), device=dev, dtype=im.dtype)
+    fn = L.lib().dmh_remap_u8 if u8 else L.lib().dmh_remap
+    with torch.cuda.device(dev):
+        L.check(fn(_p(im), _p(mp), _p(out), B, Cc, Hs, Ws, h, w, int(channels_last), int(bool(displacement)), _stream(dev)), "remap")
     return out
 
 

@@ -270,6 +270,15 @@ DMH_API int dmh_warp_perspective(const float* src, const double* H, float* dst, 
  * sample batches): OpenCV's fixed-point remap, weights (1-fy)(1-fx) * 2^15, (sum + 2^14) >> 15; bit-identical to cv2. */
 DMH_API int dmh_warp_perspective_u8(const uint8_t* src, const double* H, uint8_t* dst, int B, int C, int Hs, int Ws,
                             int h, int w, int channels_last, void* stream);
+/* cv2.remap(img, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT 0), batched: remap_using_correspondence_map
+ * (HEM/utils_operations/pixel_wise_mapping.py:35-52; displacement = 0, map = absolute coordinates) and
+ * remap_using_flow_fields (pixel_wise_mapping.py:7-32; displacement = 1, map = flow, the pixel grid is added).
+ * map: (B,2,h,w) fp32 (x then y); src / dst as in dmh_warp_perspective.  Coordinates fixed to 1/32 px as OpenCV does
+ * (cvRound(v * 32), integer part saturated to int16); bit-identical to cv2 for fp32 and uint8 images. */
+DMH_API int dmh_remap(const float* src, const float* map, float* dst, int B, int C, int Hs, int Ws, int h, int w,
+              int channels_last, int displacement, void* stream);
+DMH_API int dmh_remap_u8(const uint8_t* src, const float* map, uint8_t* dst, int B, int C, int Hs, int Ws, int h, int w,
+                 int channels_last, int displacement, void* stream);
 
 /* --- evaluation metric (A18) --------------------------------------------------------------- */
 /* compute_eval_results(): per sample mean over P points of min(err(p1->p2, flow_f), err(p2->p1, flow_b)),

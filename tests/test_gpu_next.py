@@ -272,3 +272,38 @@ def test_warp_perspective_u8_matches_cv2_bit_for_bit():
         assert np.array_equal(out[i], cv2.warpPerspective(img[i].numpy(), Hm[i], (132, 100)))
     samples = dgm.split_sample_batches([{"imgs": imgs[:2], "homos": homos[:2]}, {"imgs": imgs[2:], "homos": homos[2:]}])
     assert len(samples) == N and samples[3]["img12"].shape == (6, h, w) and np.array_equal(samples[3]["homo12"], homos[3])
+
+
+def test_remap_matches_cv2():
+    """remap_using_flow_fields / remap_using_correspondence_map (HEM/utils_operations/pixel_wise_mapping.py:7-52) against
+    cv2.remap itself, fp32 and uint8 images, 1 / 3 channels, coordinates inside, on the border, far outside, non-finite:
+    bit-identical."""
+    from dmhomo_b200.compat import pixel_wise_mapping as pwm
+
+    rs = np.random.default_rng(5)
+    for (h, w, c) in ((48, 80, 3), (37, 53, 1), (64, 64, 3)):
+        img_f = rs.random((h, w, c), dtype=np.float32) if c > 1 else rs.random((h, w), dtype=np.float32)
+        img_u = rs.integers(0, 256, size=img_f.shape, dtype=np.uint8)
+        dx = (rs.standard_normal((h, w)) * 6).astype(np.float32)
+        dy = (rs.standard_normal((h, w)) * 6).astype(np.float32)
+        dx[::9, ::7] += 500.0
+        dy[3::11, 2::5] -= 70000.0          # beyond OpenCV's int16 coordinate range
+        dx[5, 5], dy[6, 6] = np.inf, np.nan
+        dx[7, 7] = -3.0e9
+        for img in (img_f, img_u):
+            ref = port.remap_using_flow_fields(img, dx, dy)
+            out = pwm.remap_using_flow_fields(img, dx, dy)
+            assert out.dtype == ref.dtype and out.shape == ref.shape
+            assert np.array_equal(out, ref), (h, w, c, img.dtype)
+            X, Y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+            mx, my = (X * 0.9 + 2.25 + dx * 0.1).astype(np.float32), (Y * 1.05 - 1.5).astype(np.float32)
+            assert np.array_equal(pwm.remap_using_correspondence_map(img, mx, my), port.remap_using_correspondence_map(img, mx, my))
+    # batched tensor form, planar layout
+    B, C, h, w = 3, 3, 40, 56
+    img = torch.rand(B, C, h, w, generator=g(401))
+    coords = torch.rand(B, 2, h, w, generator=g(402)) * torch.tensor([w + 8.0, h + 8.0]).view(1, 2, 1, 1) - 4.0
+    out = ops.remap(img.to(DEV), coords.to(DEV)).cpu()
+    for b in range(B):
+        ref = port.remap_using_correspondence_map(img[b].permute(1, 2, 0).contiguous().numpy(), coords[b, 0].numpy(), coords[b, 1].numpy())
+        assert np.array_equal(out[b].permute(1, 2, 0).numpy(), ref)
+

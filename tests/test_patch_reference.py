@@ -48,8 +48,11 @@ for root in (mods, hem):
     for n in ("get_warp_flow", "get_grid", "upsample2d_flow_as"):
         assert getattr(root["model.net"], n) is getattr(hem_utils, n), ("model.net", n)
     assert root["model.swin_multi"].get_warp_flow is hem_utils.get_warp_flow
-for n in pixel_wise_mapping.__all__:
+for n in ("warp", "warp_with_mapping"):
     assert getattr(mods["utils_operations.pixel_wise_mapping"], n) is getattr(pixel_wise_mapping, n)
+# the cv2 remap helpers serve the loaders' host-side augmentation (flow_and_mapping_operations.py:74-81): left alone
+for n in ("remap_using_flow_fields", "remap_using_correspondence_map"):
+    assert not is_ours(getattr(mods["utils_operations.pixel_wise_mapping"], n)), n
 for n in ("get_gt_correspondence_mask", "create_border_mask", "from_homography_to_pixel_wise_mapping"):
     assert getattr(mods["utils_operations.flow_and_mapping_operations"], n) is getattr(fmo, n)
 # HEM/loss/losses.py imports the mask helpers it calls in compute_losses by value
