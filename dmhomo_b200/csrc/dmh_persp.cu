@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) warp_persp_kernel(const T* __restrict__ s
   sy = Y >> 5;
   }
   const int iax = X & 31, iay = Y & 31;
-  const float ax = div_rn((float)iax, 32.0f), ay = div_rn((float)iay, 32.0f);
+  const float ax = mul_rn((float)iax, 0.03125f), ay = mul_rn((float)iay, 0.03125f);   // i / 32, exact either way
   const float bx0 = sub_rn(1.0f, ax), by0 = sub_rn(1.0f, ay);
   const float w00 = mul_rn(by0, bx0), w01 = mul_rn(by0, ax), w10 = mul_rn(ay, bx0), w11 = mul_rn(ay, ax);
   // (1-fy)(1-fx) * 2^15 with fx, fy multiples of 1/32: (32-iay)(32-iax) * 32, exact
