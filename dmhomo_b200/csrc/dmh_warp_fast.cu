@@ -393,6 +393,58 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
   }
 }
 
+// Forward warp of a feature map with many channels by an explicit flow (the Swin pyramid levels, C = 12 / 24 at
+// 80 x 144 and below, HEM/model/swin_multi.py:161-166): one thread per output pixel - coordinate, mask and taps once,
+// then the channels in a loop (four coalesced loads, the sampler's own blend, one store each).  The tiled kernel above
+// walks 16 rows per thread on 64 x 64 tiles, which leaves half the threads of such small planes idle and pays the
+// coordinate arithmetic once per group of three channels: 68 us vs this kernel on 64 x 12 x 80 x 144.
+template <int SAMPLER>
+__global__ void __launch_bounds__(NT) warp_flow_channels_fwd_kernel(const __grid_constant__ FastArgs a, int C) {
+  const FastTerm tm = (blockIdx.z == 0) ? a.t[0] : a.t[1];
+  const int h = a.h, w = a.w, Hs = a.Hs, Ws = a.Ws;
+  const unsigned plane_o = (unsigned)(h * w), plane_s = (unsigned)(Hs * Ws);
+  const float wf = (float)w, hf = (float)h;
+  DMH_PLANE_LOOP(b, p, a.B, plane_o) {
+    const int y = (int)(p / (unsigned)w), x = (int)(p - (unsigned)y * (unsigned)w);
+    const float xf = (float)x, yf = (float)y;
+    const float gx = add_rn(xf, a.sx), gy = add_rn(yf, a.sy);
+    const float* fl = tm.param + (size_t)b * 2 * plane_o;
+    const float fx = __ldg(fl + p), fy = __ldg(fl + plane_o + p);
+    const float cx = add_rn(gx, fx), cy = add_rn(gy, fy);
+    if (tm.valid) {
+      const float mx = add_rn(fx, xf), my = add_rn(fy, yf);
+      tm.valid[(size_t)b * plane_o + p] = ((mx >= 0.f) && (mx <= wf) && (my >= 0.f) && (my <= hf)) ? 1 : 0;
+    }
+    Taps tp;
+    int x0, y0, x1, y1;
+    make_taps<SAMPLER>(cx, cy, Hs, Ws, tp, x0, y0, x1, y1);
+    tp.wa = mul_rn(tp.ax1, tp.ay1);
+    tp.wb = mul_rn(tp.ax1, tp.ay0);
+    tp.wc = mul_rn(tp.ax0, tp.ay1);
+    tp.wd = mul_rn(tp.ax0, tp.ay0);
+    const float* __restrict__ sp = tm.src + (size_t)b * C * plane_s;
+    float* __restrict__ op = tm.out + (size_t)b * C * plane_o + p;
+    // four channels at a time: their sixteen loads are issued before the first blend (a store between two channels
+    // would otherwise order the next channel's loads behind it)
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      float I[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* sc = sp + (size_t)(c + k) * plane_s;
+        I[k][0] = __ldg(sc + tp.ia); I[k][1] = __ldg(sc + tp.ib); I[k][2] = __ldg(sc + tp.ic); I[k][3] = __ldg(sc + tp.id);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) op[(size_t)(c + k) * plane_o] = blend<SAMPLER>(tp, I[k][0], I[k][1], I[k][2], I[k][3]);
+    }
+    for (; c < C; ++c) {
+      const float* sc = sp + (size_t)c * plane_s;
+      const float Ia = __ldg(sc + tp.ia), Ib = __ldg(sc + tp.ib), Ic = __ldg(sc + tp.ic), Id = __ldg(sc + tp.id);
+      op[(size_t)c * plane_o] = blend<SAMPLER>(tp, Ia, Ib, Ic, Id);
+    }
+  }
+}
+
 template <int SAMPLER, int PARAM, int PASS, int CT, int LOSS>
 int launch(const FastArgs& a, int n, long long tiles, int flags, cudaStream_t stream) {
   dim3 grid((unsigned)tiles, (unsigned)n, 1);
@@ -542,6 +594,19 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
       FastArgs at = a;
       const int rc = warp_tile_launch(at, n, mode, d0.C, true, stream);
       if (rc != 1) return rc;
+    }
+  }
+  if (groups > 1 && pass == PASS_FWD && d0.param_kind == DMH_PARAM_FLOW && loss == DMH_LOSS_NONE) {
+    bool plain = true;
+    for (int i = 0; i < n; ++i) plain = plain && d[i].out && !d[i].soft_mask;
+    if (plain) {
+      const dim3 g = plane_grid((long long)d0.h * d0.w, d0.B, NT);
+      const dim3 grid(g.x, g.y, (unsigned)n);
+      if (d0.sampler == DMH_S1)
+        warp_flow_channels_fwd_kernel<DMH_S1><<<grid, NT, 0, stream>>>(a, d0.C);
+      else
+        warp_flow_channels_fwd_kernel<DMH_S3_BORDER><<<grid, NT, 0, stream>>>(a, d0.C);
+      return launched("warp_flow_channels_fwd_kernel");
     }
   }
   if (groups > 1 && pass != PASS_FWD && d0.param_kind == DMH_PARAM_FLOW) {

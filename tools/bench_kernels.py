@@ -75,13 +75,24 @@ def main():
             ms = timeit(lambda img, H: ops.warp(img, H, kind=ops.PARAM_HOMOGRAPHY, return_mask=True), sets)
             row(name, ms, B * h * w, 8 * C + 1)
         # explicit flow parameterisation (drop-in get_warp_flow): 8C + 8 B/px
+        # flows: what HEM predicts (a smooth 8-basis flow, weights U(-4, 4)) and, as the worst case for a gather, per-pixel noise
+        def basis_flow(B, h, w):
+            bs = hem_utils.gen_basis(h, w).to(DEV)
+            return ops.basis_combine(bs, (torch.rand(B, 8, generator=gen, device=DEV) * 2 - 1) * 4.0, h, w)
+
         B, C, h, w = 64, 1, 320, 576
+        sets = [(torch.rand(B, C, h, w, generator=gen, device=DEV), basis_flow(B, h, w)) for _ in range(4)]
+        row("get_warp_flow(img, basis flow) S1              B=64 C=1 320x576", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
+            B * h * w, 8 * C + 8)
         sets = [(torch.rand(B, C, h, w, generator=gen, device=DEV), torch.randn(B, 2, h, w, generator=gen, device=DEV) * 8) for _ in range(4)]
-        row("get_warp_flow(img, flow) S1                    B=64 C=1 320x576", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
+        row("get_warp_flow(img, noise flow sigma 8) S1      B=64 C=1 320x576", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
             B * h * w, 8 * C + 8)
         B, C, h, w = 64, 12, 80, 144
+        sets = [(torch.rand(B, C, h, w, generator=gen, device=DEV), basis_flow(B, h, w)) for _ in range(6)]
+        row("get_warp_flow(feat, basis flow) pyramid level  B=64 C=12 80x144", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
+            B * h * w, 8 * C + 8)
         sets = [(torch.rand(B, C, h, w, generator=gen, device=DEV), torch.randn(B, 2, h, w, generator=gen, device=DEV) * 4) for _ in range(6)]
-        row("get_warp_flow(feat, flow) pyramid level        B=64 C=12 80x144", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
+        row("get_warp_flow(feat, noise flow sigma 4)        B=64 C=12 80x144", timeit(lambda i, f: hem_utils.get_warp_flow(i, f), sets),
             B * h * w, 8 * C + 8)
         # homography -> flow (fp32, bit-exact chain): 8 B/px written
         B, h, w = 256, 320, 576
@@ -103,8 +114,10 @@ def main():
         row("cfg3 flow_to_image (HSV wheel)                  B=400 256x256", timeit(lambda f: ops.flow_to_rgb(f, in_channels_last=True, out_channels_last=True), fl), B * h * w, 20)
         im = [(torch.rand(B, 3, h, w, generator=gen, device=DEV), H64[k]) for k in range(2)]
         row("cfg3 warpPerspective (cv2-exact S4)             B=400 C=3 256x256", timeit(lambda i, H: ops.warp_perspective(i, H, (w, h)), im), B * h * w, 24)
+        sets = [(torch.rand(B, 3, h, w, generator=gen, device=DEV), ops.homography_to_flow_f64(H64[k], h, w, eps=1e-6, channels_last=False)) for k in range(2)]
+        row("cfg3 flow_warp (S3 border, homography flow)     B=400 C=3 256x256", timeit(lambda i, f: dgm.flow_warp(i, f), sets), B * h * w, 8 * 3 + 8)
         sets = [(torch.rand(B, 3, h, w, generator=gen, device=DEV), torch.randn(B, 2, h, w, generator=gen, device=DEV) * 6) for _ in range(2)]
-        row("cfg3 flow_warp (S3 border)                      B=400 C=3 256x256", timeit(lambda i, f: dgm.flow_warp(i, f), sets), B * h * w, 8 * 3 + 8)
+        row("cfg3 flow_warp (S3 border, noise flow sigma 6)  B=400 C=3 256x256", timeit(lambda i, f: dgm.flow_warp(i, f), sets), B * h * w, 8 * 3 + 8)
         # section 8f rows
         B, H_, W_ = 64, 360, 640
         u8 = [(torch.randint(0, 256, (B, 6, H_, W_), generator=gen, device=DEV, dtype=torch.uint8),
