@@ -26,6 +26,7 @@ int* tuning_slot(const char* key) {
   if (!strcmp(key, "tile_interior")) return &t.tile_interior;
   if (!strcmp(key, "tile_flow")) return &t.tile_flow;
   if (!strcmp(key, "tile_wide")) return &t.tile_wide;
+  if (!strcmp(key, "channels")) return &t.channels;
   if (!strcmp(key, "tile_pair_major")) return &t.tile_pair_major;
   if (!strcmp(key, "tile_dyn")) return &t.tile_dyn;
   if (!strcmp(key, "tile_chunk")) return &t.tile_chunk;

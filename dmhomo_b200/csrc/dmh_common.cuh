@@ -45,6 +45,7 @@ struct Tuning {
   int tile = 3;           // 0: scalar kernels only; 1: TMA tile kernel for the dense C = 1 launches; 2: also the gradient-free C = 3 launches; 3: also the C = 3 training launch
   int tile_interior = 3;  // bit 0: interior-tile body, bit 1: mixed (per-row-pair vote) body
   int tile_flow = 1;      // explicit-flow C = 1 launches on the tile kernel (0: scalar kernels)
+  int channels = 1;       // pixel-per-thread forward kernel for explicit-flow warps of feature maps with C other than 1 / 3 (0: channel groups)
   int tile_wide = 0;      // (-DDMH_TILE_WIDE variant builds only) gradient-free C = 1 launches on the 24-consumer-warp geometry
   int tile_pair_major = -1; // two-term launches walk (sample, term, tile) instead of (term, sample, tile); -1: at C = 3
   int tile_dyn = -1;      // share (percent) of the tile list handed out dynamically (guided: long runs first, single tiles last); -1: per launch kind

@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(NT, (TUNE >> 8) & 15) warp_fast_kernel(const _
 // 80 x 144 and below, HEM/model/swin_multi.py:161-166): one thread per output pixel - coordinate, mask and taps once,
 // then the channels in a loop (four coalesced loads, the sampler's own blend, one store each).  The tiled kernel above
 // walks 16 rows per thread on 64 x 64 tiles, which leaves half the threads of such small planes idle and pays the
-// coordinate arithmetic once per group of three channels: 68 us vs this kernel on 64 x 12 x 80 x 144.
+// coordinate arithmetic once per group of three channels: 68 us 46 us vs 26 us here on 64 x 12 x 80 x 144 under a basis flow.
+// (The adjoint stays on the tiled kernel, channel group by channel group: its vertical tap merging halves the REDs -
+// a pixel-per-thread adjoint with four REDs per channel and pixel measured 122 us against 69 us.)
 template <int SAMPLER>
 __global__ void __launch_bounds__(NT) warp_flow_channels_fwd_kernel(const __grid_constant__ FastArgs a, int C) {
   const FastTerm tm = (blockIdx.z == 0) ? a.t[0] : a.t[1];
@@ -596,7 +598,7 @@ int warp_fast_try(const dmh_warp_desc* d, int n, int pass, cudaStream_t stream) 
       if (rc != 1) return rc;
     }
   }
-  if (groups > 1 && pass == PASS_FWD && d0.param_kind == DMH_PARAM_FLOW && loss == DMH_LOSS_NONE) {
+  if (groups > 1 && pass == PASS_FWD && d0.param_kind == DMH_PARAM_FLOW && loss == DMH_LOSS_NONE && (tuning().channels & 1)) {
     bool plain = true;
     for (int i = 0; i < n; ++i) plain = plain && d[i].out && !d[i].soft_mask;
     if (plain) {

@@ -146,6 +146,8 @@ DMH_API const char* dmh_last_kernel_name(void);
  *                   (default -1: 0 for the C = 1 training launch, 100 otherwise)
  *   "tile_chunk"    longest run of tiles per dynamic claim, 1 .. 8; runs shrink to single tiles at the end
  *                   (default -1: 1 for the C = 1 training launch, 8 otherwise)
+ *   "channels"      1 (default): the pixel-per-thread forward kernel for explicit-flow warps of feature maps with C other
+ *                   than 1 / 3; 0: channel groups on the tiled scalar kernel (which the backward always uses)
  *   "tile_wide"     accepted, without effect in the product library (a 24-consumer-warp geometry of experiment builds)
  * The library reads no environment variables.  Unknown key: DMH_EINVAL. */
 DMH_API int dmh_set_tuning(const char* key, int value);
